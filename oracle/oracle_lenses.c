@@ -1,0 +1,539 @@
+/* TEST INFRASTRUCTURE — parity oracle, not part of the product.  See blinky_oracle.h.
+ *
+ * Literal C transcriptions of shipped Blinky lens and globe scripts
+ * (/root/reference/game/lua-scripts/{lenses,globes}/<name>.lua).  A Lua 5.2 VM
+ * executes those scripts as IEEE-double operations in source order with
+ * libm for math.*; these functions perform the same operations in the same
+ * order, so a correct Lua evaluator must reproduce their results BIT FOR BIT.
+ * That is how the product's own Lua-subset evaluator (no real Lua exists in the
+ * build image) is pinned independently of itself.
+ *
+ * Compiled with -ffp-contract=off and no -ffast-math.  `pi` is math.pi.
+ */
+#include <math.h>
+#include <string.h>
+
+#include "blinky_oracle.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+static const double pi = M_PI;
+
+/* ---- lenses/panini.lua ---------------------------------------------------- */
+static const double panini_d = 1; /* :1 */
+
+static int panini_inverse(double x, double y, double r[3], void *ud)
+{ /* :8-17 */
+    (void)ud;
+    double d = panini_d;
+    double k = x * x / ((d + 1) * (d + 1));
+    double dscr = k * k * d * d - (k + 1) * (k * d * d - 1);
+    double clon = (-k * d + sqrt(dscr)) / (k + 1);
+    double S = (d + 1) / (d + clon);
+    double lon = atan2(x, S * clon);
+    double lat = atan2(y, S);
+    orc_lua_latlon_to_ray(lat, lon, r);
+    return 1;
+}
+
+static int panini_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :19-25 */
+    (void)ud;
+    double d = panini_d, lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double S = (d + 1) / (d + cos(lon));
+    *ox = S * sin(lon);
+    *oy = S * tan(lat);
+    return 1;
+}
+
+/* ---- lenses/stereographic.lua --------------------------------------------- */
+static const double stereo_angleScale = 0.5; /* :1 */
+
+static int stereographic_inverse(double x, double y, double o[3], void *ud)
+{ /* :8-14 — r == 0 at the centre pixel gives NaN, by design of the script */
+    (void)ud;
+    double r = sqrt(x * x + y * y);
+    double theta = atan(r) / stereo_angleScale;
+    double s = sin(theta);
+    o[0] = x / r * s;
+    o[1] = y / r * s;
+    o[2] = cos(theta);
+    return 1;
+}
+
+static int stereographic_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :16-23 */
+    (void)ud;
+    double theta = acos(z);
+    double r = tan(theta * stereo_angleScale);
+    double c = r / sqrt(x * x + y * y);
+    *ox = x * c;
+    *oy = y * c;
+    return 1;
+}
+
+/* ---- lenses/rectilinear.lua ----------------------------------------------- */
+static int rectilinear_inverse(double x, double y, double o[3], void *ud)
+{ /* :7-14 */
+    (void)ud;
+    double r = sqrt(x * x + y * y);
+    double theta = atan(r);
+    double s = sin(theta);
+    o[0] = x / r * s;
+    o[1] = y / r * s;
+    o[2] = cos(theta);
+    return 1;
+}
+
+static int rectilinear_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :16-23 */
+    (void)ud;
+    double theta = acos(z);
+    double r = tan(theta);
+    double c = r / sqrt(x * x + y * y);
+    *ox = x * c;
+    *oy = y * c;
+    return 1;
+}
+
+/* ---- lenses/equirect.lua --------------------------------------------------- */
+static int equirect_inverse(double x, double y, double o[3], void *ud)
+{ /* :9-16 */
+    (void)ud;
+    if (fabs(y) > pi / 2 || fabs(x) > pi) return 0;
+    double lon = x;
+    double lat = y;
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int equirect_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :18-23 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon;
+    *oy = lat;
+    return 1;
+}
+
+/* ---- lenses/cylinder.lua --------------------------------------------------- */
+static int cylinder_inverse(double x, double y, double o[3], void *ud)
+{ /* :8-15 */
+    (void)ud;
+    if (fabs(x) > pi) return 0;
+    double lon = x;
+    double lat = atan(y);
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int cylinder_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :17-22 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon;
+    *oy = tan(lat);
+    return 1;
+}
+
+/* ---- lenses/mercator.lua --------------------------------------------------- */
+static int mercator_inverse(double x, double y, double o[3], void *ud)
+{ /* :12-19 */
+    (void)ud;
+    if (fabs(x) > pi) return 0;
+    double lon = x;
+    double lat = atan(sinh(y));
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int mercator_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :22-27 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon;
+    *oy = log(tan(pi * 0.25 + lat * 0.5));
+    return 1;
+}
+
+/* ---- lenses/hammer.lua ----------------------------------------------------- */
+static int hammer_inverse(double x, double y, double o[3], void *ud)
+{ /* :9-17 */
+    (void)ud;
+    if (x * x / 8 + y * y / 2 > 1) return 0;
+    double z = sqrt(1 - 0.0625 * x * x - 0.25 * y * y);
+    double lon = 2 * atan(z * x / (2 * (2 * z * z - 1)));
+    double lat = asin(z * y);
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int hammer_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :19-24 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = 2 * sqrt(2) * cos(lat) * sin(lon * 0.5) / sqrt(1 + cos(lat) * cos(lon * 0.5));
+    *oy = sqrt(2) * sin(lat) / sqrt(1 + cos(lat) * cos(lon * 0.5));
+    return 1;
+}
+
+/* ---- lenses/fisheye1.lua --------------------------------------------------- */
+static int fisheye1_inverse(double x, double y, double o[3], void *ud)
+{ /* :9-20 */
+    (void)ud;
+    double r = sqrt(x * x + y * y);
+    if (r > pi) return 0;
+    double theta = r;
+    double s = sin(theta);
+    o[0] = x / r * s;
+    o[1] = y / r * s;
+    o[2] = cos(theta);
+    return 1;
+}
+
+static int fisheye1_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :22-29 */
+    (void)ud;
+    double theta = acos(z);
+    double r = theta;
+    double c = r / sqrt(x * x + y * y);
+    *ox = x * c;
+    *oy = y * c;
+    return 1;
+}
+
+/* ---- lenses/fisheye2.lua --------------------------------------------------- */
+static int fisheye2_inverse(double x, double y, double o[3], void *ud)
+{ /* :11-23 */
+    (void)ud;
+    double maxr = 2 * sin(pi * 0.5); /* :1 */
+    double r = sqrt(x * x + y * y);
+    if (r > maxr) return 0;
+    double theta = 2 * asin(r * 0.5);
+    double s = sin(theta);
+    o[0] = x / r * s;
+    o[1] = y / r * s;
+    o[2] = cos(theta);
+    return 1;
+}
+
+static int fisheye2_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :25-32 */
+    (void)ud;
+    double theta = acos(z);
+    double r = 2 * sin(theta * 0.5);
+    double c = r / sqrt(x * x + y * y);
+    *ox = x * c;
+    *oy = y * c;
+    return 1;
+}
+
+/* ---- lenses/sinusoidal.lua, winkel1.lua (forward-only) ---------------------- */
+static int sinusoidal_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* sinusoidal.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon * cos(lat);
+    *oy = lat;
+    return 1;
+}
+
+static int winkel1_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* winkel1.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon * (2 / pi + cos(lat)) / 2;
+    *oy = lat;
+    return 1;
+}
+
+/* ---- lenses/quincuncial.lua ------------------------------------------------ */
+static const double q_eps = 0.0001;        /* :1 */
+#define q_halfpi (pi / 2)                  /* :2 */
+
+static double q_asqrt(double x)
+{ /* :9-14 */
+    if (x > 0) return sqrt(x);
+    return 0;
+}
+
+/* :15-62; returns sn, cn, dn (the 4th result, ph, is unused by callers) */
+static void q_ellipj(double u, double m, double *sn, double *cn, double *dn)
+{
+    double ai, b, phi, t, twon;
+    if (m < q_eps) { /* :17-25 */
+        t = sin(u);
+        b = cos(u);
+        ai = .25 * m * (u - t * b);
+        *sn = t - ai * b;
+        *cn = b + ai * t;
+        *dn = 1 - .5 * m * t * t;
+        return;
+    }
+    if (m >= 1 - q_eps) { /* :26-36 */
+        ai = .25 * (1 - m);
+        b = cosh(u);
+        t = tanh(u);
+        phi = 1 / b;
+        twon = b * sinh(u);
+        *sn = t + ai * (twon - u) / (b * b);
+        *cn = phi - ai * t * phi * (twon - u);
+        *dn = phi + ai * t * phi * (twon + u);
+        return;
+    }
+    double a[10] = {0, 1, 0, 0, 0, 0, 0, 0, 0, 0}; /* 1-based like the Lua tables (:38-39) */
+    double c[10] = {0, sqrt(m), 0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 1;
+    b = sqrt(1 - m);
+    twon = 1;
+    while (fabs(c[i] / a[i]) > q_eps && i < 9) { /* :44-51 */
+        ai = a[i];
+        i = i + 1;
+        c[i] = .5 * (ai - b);
+        a[i] = .5 * (ai + b);
+        b = q_asqrt(ai * b);
+        twon = twon * 2;
+    }
+    phi = twon * a[i] * u; /* :53 */
+    do {                   /* :54-59 */
+        b = phi;
+        t = c[i] * sin(b) / a[i];
+        phi = .5 * (asin(t) + phi);
+        i = i - 1;
+    } while (!(i == 1));
+    t = cos(phi);
+    *sn = sin(phi);
+    *cn = t;
+    *dn = t / cos(phi - b);
+}
+
+static void q_cnrectify(double x, double y, double *latp, double *longd)
+{ /* :74-104 */
+    double sqrt2 = sqrt(2);       /* :69 */
+    double sqrt22 = sqrt2 / 2;    /* :70 */
+    double m = 1.0 / 2;           /* :71 */
+    double ke = 1.85407467730137; /* :72 */
+    double xpr = ke * (sqrt22 * x - sqrt22 * y) / sqrt2 + ke;
+    double ypr = ke * (sqrt22 * x + sqrt22 * y) / sqrt2;
+    double x1, y1;
+    if (fabs(ypr) < q_eps) {
+        double sni, cni, dni;
+        q_ellipj(xpr, m, &sni, &cni, &dni);
+        x1 = cni;
+        y1 = 0.0;
+    } else {
+        double phi = xpr, psi = ypr;
+        double s, c, d, s1, c1, d1;
+        q_ellipj(phi, m, &s, &c, &d);
+        q_ellipj(psi, 1 - m, &s1, &c1, &d1);
+        double delta = pow(c1, 2) + m * pow(s, 2) * pow(s1, 2);
+        x1 = (c * c1) / delta;
+        y1 = -(s * d * s1 * d1) / delta;
+    }
+    *longd = atan2(y1, x1);
+    *latp = 2 * atan2(sqrt(x1 * x1 + y1 * y1), 1) - q_halfpi;
+}
+
+static void q_rotate(double a, double b, double angle, double *a0, double *b0)
+{ /* :153-159 */
+    double c = cos(angle);
+    double s = sin(angle);
+    *a0 = a * c - b * s;
+    *b0 = a * s + b * c;
+}
+
+static int q_inverse_intermediate(double x, double y, double o[3])
+{ /* :161-172 */
+    if (fabs(x) > 2 || fabs(y) > 1) return 0;
+    x = x + 1;
+    double lat, lon, r[3];
+    q_cnrectify(x, y, &lat, &lon);
+    orc_lua_latlon_to_ray(lat, -lon, r);
+    o[0] = r[0];
+    o[1] = r[2];
+    o[2] = -r[1];
+    return 1;
+}
+
+static int quincuncial_inverse(double x, double y, double o[3], void *ud)
+{ /* :174-210 */
+    (void)ud;
+    double sqrt2 = sqrt(2);
+    if (fabs(x) > sqrt2 || fabs(y) > sqrt2) return 0;
+    double x0, y0;
+    if (fabs(x) + fabs(y) < sqrt2) {
+        q_rotate(x, y, pi / 4, &x0, &y0);
+        x0 = x0 - 1;
+    } else if (x > 0 && y < 0) {
+        q_rotate(x, y, pi / 4, &x0, &y0);
+        x0 = x0 - 1;
+    } else if (x < 0 && y > 0) {
+        q_rotate(x, y, pi / 4, &x0, &y0);
+        x0 = x0 + 3;
+    } else if (x < 0 && y < 0) {
+        q_rotate(x, y, pi / 4 + pi, &x0, &y0);
+        x0 = x0 + 1;
+        y0 = y0 - 2;
+    } else {
+        q_rotate(x, y, pi / 4 + pi, &x0, &y0);
+        x0 = x0 + 1;
+        y0 = y0 + 2;
+    }
+    return q_inverse_intermediate(x0, y0, o);
+}
+
+/* ---- registry --------------------------------------------------------------- */
+int orc_find_lens(const char *name, orc_lens_def *out)
+{
+    memset(out, 0, sizeof *out);
+    out->name = name;
+    if (!strcmp(name, "panini")) {
+        out->inverse = panini_inverse; out->forward = panini_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->onload = "f_fov 180";
+    } else if (!strcmp(name, "stereographic")) {
+        out->inverse = stereographic_inverse; out->forward = stereographic_forward;
+        out->max_fov = 360; out->max_vfov = 360; out->onload = "f_fov 180";
+    } else if (!strcmp(name, "rectilinear")) {
+        out->inverse = rectilinear_inverse; out->forward = rectilinear_forward;
+        out->max_fov = 180; out->max_vfov = 180; out->onload = "f_fov 110";
+    } else if (!strcmp(name, "equirect")) {
+        out->inverse = equirect_inverse; out->forward = equirect_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "cylinder")) {
+        out->inverse = cylinder_inverse; out->forward = cylinder_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->onload = "f_cover";
+    } else if (!strcmp(name, "mercator")) {
+        out->inverse = mercator_inverse; out->forward = mercator_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->onload = "f_cover";
+    } else if (!strcmp(name, "hammer")) {
+        out->inverse = hammer_inverse; out->forward = hammer_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = 2 * sqrt(2) * 2; out->lens_height = sqrt(2) * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "fisheye1")) {
+        out->inverse = fisheye1_inverse; out->forward = fisheye1_forward;
+        out->max_fov = 360; out->max_vfov = 360; out->lens_width = 2 * pi; out->lens_height = 2 * pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "fisheye2")) {
+        double maxr = 2 * sin(pi * 0.5);
+        out->inverse = fisheye2_inverse; out->forward = fisheye2_forward;
+        out->max_fov = 360; out->max_vfov = 360; out->lens_width = maxr * 2; out->lens_height = maxr * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "quincuncial")) {
+        double sqrt2 = sqrt(2);
+        out->inverse = quincuncial_inverse;
+        out->lens_width = 2 * sqrt2; out->lens_height = 2 * sqrt2; out->onload = "f_contain";
+    } else if (!strcmp(name, "sinusoidal")) {
+        out->forward = sinusoidal_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "winkel1")) {
+        out->forward = winkel1_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = pi * (2 / pi + 1) / 2 * 2; out->lens_height = pi; out->onload = "f_contain";
+    } else {
+        return 0;
+    }
+    return 1;
+}
+
+/* ---- globes ------------------------------------------------------------------ */
+static void set_plate(orc_globe *g, int i, double fx, double fy, double fz, double ux, double uy, double uz, double fov)
+{
+    double f[3] = {fx, fy, fz}, u[3] = {ux, uy, uz};
+    orc_globe_set_plate(g, i, f, u, fov);
+}
+
+static const double kCube[6][6] = {
+    /* globes/cube.lua:3-10 forward, up */
+    {0, 0, 1, 0, 1, 0}, {1, 0, 0, 0, 1, 0}, {-1, 0, 0, 0, 1, 0},
+    {0, 0, -1, 0, 1, 0}, {0, 1, 0, 0, 0, -1}, {0, -1, 0, 0, 0, 1},
+};
+
+/* globes/fast.lua:10-27 */
+static int fast_globe_plate(double x, double y, double z, int *plate, void *ud)
+{
+    (void)ud;
+    double big_fov = 160;
+    if (z <= 0) return 0; /* return nil */
+    double dist = 0.5 / tan(big_fov * pi / 180 / 2);
+    double size = 2 * dist * tan(pi / 4);
+    double u = x / z * dist;
+    double v = y / z * dist;
+    if (fabs(u) < size / 2 && fabs(v) < size / 2) *plate = 0; /* small */
+    else *plate = 1;                                        /* big */
+    return 1;
+}
+
+int orc_load_globe(const char *name, orc_globe *g)
+{
+    int ps = g->platesize;
+    memset(g, 0, sizeof *g);
+    g->platesize = ps;
+    if (!strcmp(name, "cube") || !strcmp(name, "cube_edge") || !strcmp(name, "cube_corner")) {
+        int corner = !strcmp(name, "cube_corner"), edge = !strcmp(name, "cube_edge");
+        g->numplates = 6;
+        for (int i = 0; i < 6; i++) {
+            double p[2][3] = {{kCube[i][0], kCube[i][1], kCube[i][2]}, {kCube[i][3], kCube[i][4], kCube[i][5]}};
+            if (corner || edge) { /* cube_edge.lua:16-32, cube_corner.lua:16-40 */
+                double a = pi / 4;
+                for (int k = 0; k < 2; k++) {
+                    double x = p[k][0], z = p[k][2];
+                    p[k][0] = x * cos(a) - z * sin(a);
+                    p[k][2] = x * sin(a) + z * cos(a);
+                    if (corner) {
+                        double y = p[k][1];
+                        z = p[k][2];
+                        p[k][1] = y * cos(a) - z * sin(a);
+                        p[k][2] = y * sin(a) + z * cos(a);
+                    }
+                }
+            }
+            orc_globe_set_plate(g, i, p[0], p[1], 90);
+        }
+        return 1;
+    }
+    if (!strcmp(name, "trism")) { /* globes/trism.lua:2-8 */
+        g->numplates = 5;
+        set_plate(g, 0, -cos(pi / 6), 0, sin(pi / 6), 0, 1, 0, 120);
+        set_plate(g, 1, cos(pi / 6), 0, sin(pi / 6), 0, 1, 0, 120);
+        set_plate(g, 2, 0, 0, -1, 0, 1, 0, 120);
+        set_plate(g, 3, 0, 1, 0, 0, 0, -1, 128);
+        set_plate(g, 4, 0, -1, 0, 0, 0, -1, 128);
+        return 1;
+    }
+    if (!strcmp(name, "tetra")) { /* globes/tetra.lua:2-42 */
+        double tau = pi * 2; /* fisheye.c:1247 */
+        double d120 = tau / 3;
+        double d60 = d120 / 2;
+        double r = 1;
+        double s = 2 * r * sin(d60);
+        double h = sqrt(s * s - r * r);
+        double theta = acos(r / s);
+        double c = s / 2 / sin(theta);
+        double e = r * cos(d60);
+        double f = h - c;
+        double fovr = 2 * atan(r / f);
+        double fovd = fovr * 180 / pi + 1;
+        double y = e - e * e / (r + e);
+        double z = -f + h * e / (r + e);
+        g->numplates = 4;
+        set_plate(g, 0, 0, -y / f, z / f, 0, -(e - y) / e, (-f - z) / e, fovd);
+        set_plate(g, 1, y / f * sin(d120), -y / f * cos(d120), z / f, (e - y) / e * sin(d120), -(e - y) / e * cos(d120), (-f - z) / e, fovd);
+        set_plate(g, 2, y / f * sin(-d120), -y / f * cos(-d120), z / f, (e - y) / e * sin(-d120), -(e - y) / e * cos(-d120), (-f - z) / e, fovd);
+        set_plate(g, 3, 0, 0, -1, 0, -1, 0, fovd);
+        return 1;
+    }
+    if (!strcmp(name, "fast")) { /* globes/fast.lua:1-8 */
+        g->numplates = 2;
+        set_plate(g, 0, 0, 0, 1, 0, 1, 0, 90);
+        set_plate(g, 1, 0, 0, 1, 0, 1, 0, 160);
+        g->plate_fn = fast_globe_plate;
+        return 1;
+    }
+    return 0;
+}
