@@ -1,0 +1,485 @@
+// Device side of the B200 lens-warp path — kernels, resident state, frame pipeline.
+//
+// The reference's hot loop (/root/reference/engine/NQ/fisheye.c:2406-2424) is,
+// per screen pixel: load an 8-byte pointer, load the source byte through it,
+// optionally map it through a 256-entry tint LUT chosen by a second per-pixel
+// byte, store one byte.  Here one packed 32-bit lensmap entry per pixel
+// replaces pointer + tint byte (4 B instead of 9 B read per pixel), entries
+// are fetched as 128-bit vectors, source bytes are gathered through the
+// read-only path, and four output pixels are written per 32-bit store so that
+// every warp-level store instruction covers one full 128-byte line.
+//
+// sm_100a only.  HBM-bound byte work: no tensor cores on purpose.
+#include "warp_device.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../include/blinky_b200.h"
+
+namespace blinky {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunks = 4;                            // quads (4-pixel groups) per thread
+constexpr int kQuadsPerBlock = kThreads * kChunks;    // 1024 quads = 4096 pixels per CTA
+constexpr int kPixelsPerBlock = kQuadsPerBlock * 4;
+
+struct WarpParams {
+    const uint4 *lensmap4;      // packed entries, 4 per element; padded to whole CTAs
+    const uint8_t *faces;       // frame 0
+    size_t face_stride;         // bytes between frames
+    const uint32_t *bg32;       // background, 4 pixels per element (padded like the lensmap)
+    const uint8_t *lut;         // [6][256] rubix tint LUTs
+    const uint32_t *rgba;       // [256] palette expansion table (RGBA mode)
+    void *out;                  // frame 0
+    size_t out_stride;          // bytes between frames
+    uint32_t nquads;            // ceil(W*H / 4)
+    uint32_t npix;              // W*H
+};
+
+__device__ __forceinline__ uint4 ld_lensmap(const uint4 *p) {
+    // streamed once per frame by this SM: keep it out of L1 so the gathers own L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ld_face(const uint8_t *p) {
+    // read-only path, allocate in L1: neighbouring pixels hit the same sectors
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_stream_v4(uint4 *p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// --------------------------------------------------------------------------
+// K1: direct gather.  grid = (ceil(nquads/1024), nframes), block = 256.
+// Thread t of CTA b owns quads b*1024 + c*256 + t, c = 0..3, so each of the
+// four 128-bit lensmap loads of a warp covers 512 contiguous bytes and each
+// 32-bit output store of a warp covers 128 contiguous bytes.
+// --------------------------------------------------------------------------
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kThreads) warp_gather_kernel(const WarpParams p) {
+    __shared__ uint8_t s_lut[RUBIX ? 6 * 256 : 4];
+    __shared__ uint32_t s_rgba[RGBA ? 256 : 1];
+    if (RUBIX) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+        for (int i = threadIdx.x; i < 6 * 256 / 4; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    if (RGBA) {
+        for (int i = threadIdx.x; i < 256; i += kThreads) s_rgba[i] = __ldg(p.rgba + i);
+    }
+    if (RUBIX || RGBA) __syncthreads();
+
+    const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(blockIdx.y) * p.face_stride;
+    const uint32_t q0 = blockIdx.x * kQuadsPerBlock + threadIdx.x;
+
+    uint4 e[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) e[c] = ld_lensmap(p.lensmap4 + q0 + c * kThreads);  // padded: always in range
+
+    uint32_t v[kChunks][4];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const uint32_t ent[4] = {e[c].x, e[c].y, e[c].z, e[c].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[c][k] = 0;
+            if (ent[k] & BLINKY_LM_VALID) v[c][k] = ld_face(faces + (ent[k] & BLINKY_LM_INDEX_MASK));
+        }
+    }
+
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const uint32_t q = q0 + c * kThreads;
+        if (q >= p.nquads) continue;
+        const uint32_t ent[4] = {e[c].x, e[c].y, e[c].z, e[c].w};
+        const uint32_t all_valid = ent[0] & ent[1] & ent[2] & ent[3] & BLINKY_LM_VALID;
+        uint32_t bgw = 0;
+        if (!all_valid) bgw = __ldg(p.bg32 + q);
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t b = v[c][k];
+            if (RUBIX) {
+                const uint32_t t = (ent[k] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                if (t != BLINKY_LM_TINT_NONE) b = s_lut[t * 256 + b];
+            }
+            if (!(ent[k] & BLINKY_LM_VALID)) b = (bgw >> (8 * k)) & 0xffu;
+            px[k] = b;
+        }
+        if (RGBA) {
+            uint4 w = make_uint4(s_rgba[px[0]], s_rgba[px[1]], s_rgba[px[2]], s_rgba[px[3]]);
+            uint4 *o = reinterpret_cast<uint4 *>(static_cast<uint8_t *>(p.out) + static_cast<size_t>(blockIdx.y) * p.out_stride);
+            st_stream_v4(o + q, w);
+        } else {
+            uint32_t w = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+            uint32_t *o = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(p.out) + static_cast<size_t>(blockIdx.y) * p.out_stride);
+            st_stream_u32(o + q, w);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// K0: scalar kernel, one pixel per thread, byte stores.  Used only when the
+// frame size or the caller's pointers rule out 32-bit stores (W*H % 4 != 0 or
+// unaligned strides) — a correctness path for ragged sizes, not a fast path.
+// --------------------------------------------------------------------------
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams p) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= p.npix) return;
+    const uint32_t ent = __ldg(reinterpret_cast<const uint32_t *>(p.lensmap4) + i);
+    const uint8_t *faces = p.faces + static_cast<size_t>(blockIdx.y) * p.face_stride;
+    uint32_t b;
+    if (ent & BLINKY_LM_VALID) {
+        b = ld_face(faces + (ent & BLINKY_LM_INDEX_MASK));
+        if (RUBIX) {
+            const uint32_t t = (ent >> BLINKY_LM_TINT_SHIFT) & 7u;
+            if (t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
+        }
+    } else {
+        b = __ldg(reinterpret_cast<const uint8_t *>(p.bg32) + i);
+    }
+    uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(blockIdx.y) * p.out_stride;
+    if (RGBA) reinterpret_cast<uint32_t *>(o)[i] = __ldg(p.rgba + b);
+    else o[i] = static_cast<uint8_t>(b);
+}
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// frame pipeline slot
+// ---------------------------------------------------------------------------
+struct WarpDevice::Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *d_faces = nullptr, *d_out = nullptr;
+    uint8_t *h_faces = nullptr, *h_out = nullptr;  // pinned staging
+    bool busy = false;
+    // finalize info
+    uint8_t *dst = nullptr;
+    int dst_rowbytes = 0, x0 = 0, y0 = 0;
+    bool keep_unmapped = false, direct = false;
+};
+
+#define CK(call)                                      \
+    do {                                              \
+        cudaError_t e_ = (call);                      \
+        if (e_ != cudaSuccess) return fail(#call, e_); \
+    } while (0)
+
+bool WarpDevice::fail(const char *what, int cuda_err) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(static_cast<cudaError_t>(cuda_err)));
+    err_ = buf;
+    return false;
+}
+
+WarpDevice::WarpDevice(int device) : device_(device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "blinky_b200 needs an sm_100 (B200) device; device %d is sm_%d%d (%s)", device, prop.major,
+                 prop.minor, prop.name);
+        throw std::runtime_error(buf);
+    }
+    sm_count_ = prop.multiProcessorCount;
+    cudaStream_t s;
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    stream_ = s;
+    e = cudaMalloc(&d_lut_, 6 * 256);
+    if (e == cudaSuccess) e = cudaMemset(d_lut_, 0, 6 * 256);
+    if (e == cudaSuccess) e = cudaMalloc(&d_rgba_, 256 * 4);
+    if (e == cudaSuccess) e = cudaMemset(d_rgba_, 0, 256 * 4);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+}
+
+WarpDevice::~WarpDevice() {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    for (Slot *s : slots_) {
+        if (s->stream) cudaStreamDestroy(s->stream);
+        if (s->done) cudaEventDestroy(s->done);
+        cudaFree(s->d_faces);
+        cudaFree(s->d_out);
+        if (s->h_faces) cudaFreeHost(s->h_faces);
+        if (s->h_out) cudaFreeHost(s->h_out);
+        delete s;
+    }
+    cudaFree(d_lensmap_);
+    cudaFree(d_lut_);
+    cudaFree(d_bg_);
+    cudaFree(d_rgba_);
+    if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+}
+
+bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
+    CK(cudaSetDevice(device_));
+    CK(cudaDeviceSynchronize());  // nothing may still be reading the old map
+    const size_t npix = static_cast<size_t>(lm.width) * lm.height;
+    const size_t npad = round_up(npix, kPixelsPerBlock);
+    if (npad != npix_pad_) {
+        cudaFree(d_lensmap_);
+        cudaFree(d_bg_);
+        d_lensmap_ = nullptr;
+        d_bg_ = nullptr;
+        CK(cudaMalloc(&d_lensmap_, npad * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_bg_, npad));
+        CK(cudaMemset(d_bg_, 0, npad));
+    } else if (lm.width != width_ || lm.height != height_) {
+        CK(cudaMemset(d_bg_, 0, npad));
+    }
+    // padding entries are "unmapped"
+    CK(cudaMemset(d_lensmap_, 0, npad * sizeof(uint32_t)));
+    CK(cudaMemcpy(d_lensmap_, lm.packed, npix * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_lut_, lm.palmaps, 6 * 256, cudaMemcpyHostToDevice));
+    width_ = lm.width;
+    height_ = lm.height;
+    platesize_ = lm.platesize;
+    numplates_ = lm.numplates;
+    npix_ = npix;
+    npix_pad_ = npad;
+    rubix_ = lm.rubix;
+    memcpy(display_, lm.display, sizeof display_);
+    span_off_.assign(lm.span_off, lm.span_off + lm.height + 1);
+    spans_.assign(lm.spans, lm.spans + lm.nspans * 2);
+    have_lensmap_ = true;
+    // frame slots depend on the sizes: rebuild lazily
+    for (Slot *s : slots_) {
+        cudaStreamDestroy(s->stream);
+        cudaEventDestroy(s->done);
+        cudaFree(s->d_faces);
+        cudaFree(s->d_out);
+        cudaFreeHost(s->h_faces);
+        cudaFreeHost(s->h_out);
+        delete s;
+    }
+    slots_.clear();
+    return true;
+}
+
+bool WarpDevice::set_background(const uint8_t *bg_host) {
+    if (!have_lensmap_) {
+        err_ = "set_background: build a lensmap first (the background has the view's size)";
+        return false;
+    }
+    CK(cudaSetDevice(device_));
+    CK(cudaDeviceSynchronize());
+    if (bg_host) CK(cudaMemcpy(d_bg_, bg_host, npix_, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(d_bg_, 0, npix_pad_));
+    return true;
+}
+
+bool WarpDevice::set_rgba_table(const uint32_t table[256]) {
+    CK(cudaSetDevice(device_));
+    CK(cudaMemcpy(d_rgba_, table, 256 * 4, cudaMemcpyHostToDevice));
+    have_rgba_ = true;
+    return true;
+}
+
+bool WarpDevice::warp(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+                      bool rgba) {
+    if (!have_lensmap_) {
+        err_ = "warp: no lensmap on the device (call blinky_build_lensmap)";
+        return false;
+    }
+    if (nframes <= 0) return true;
+    if (nframes > 65535) {
+        err_ = "warp: at most 65535 frames per launch";
+        return false;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(stream_);
+    WarpParams p;
+    p.lensmap4 = reinterpret_cast<const uint4 *>(d_lensmap_);
+    p.faces = static_cast<const uint8_t *>(d_faces);
+    p.face_stride = face_stride;
+    p.bg32 = reinterpret_cast<const uint32_t *>(d_bg_);
+    p.lut = d_lut_;
+    p.rgba = d_rgba_;
+    p.out = d_out;
+    p.out_stride = out_stride;
+    p.nquads = static_cast<uint32_t>((npix_ + 3) / 4);
+    p.npix = static_cast<uint32_t>(npix_);
+
+    const size_t opx = rgba ? 4 : 1;  // output bytes per pixel
+    const bool vector_ok = (npix_ % 4 == 0) && (reinterpret_cast<uintptr_t>(d_out) % (4 * opx) == 0) &&
+                           (out_stride % (4 * opx) == 0 || nframes == 1);
+    const bool rubix = rubix_;
+    if (vector_ok) {
+        dim3 grid(static_cast<unsigned>(npix_pad_ / kPixelsPerBlock), static_cast<unsigned>(nframes));
+        if (rubix && rgba) warp_gather_kernel<true, true><<<grid, kThreads, 0, st>>>(p);
+        else if (rubix) warp_gather_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
+        else if (rgba) warp_gather_kernel<false, true><<<grid, kThreads, 0, st>>>(p);
+        else warp_gather_kernel<false, false><<<grid, kThreads, 0, st>>>(p);
+        char buf[160];
+        snprintf(buf, sizeof buf, "warp_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", rubix, rgba, grid.x, grid.y, kThreads);
+        last_kernel_ = buf;
+    } else {
+        dim3 grid(static_cast<unsigned>((npix_ + kThreads - 1) / kThreads), static_cast<unsigned>(nframes));
+        if (rubix && rgba) warp_scalar_kernel<true, true><<<grid, kThreads, 0, st>>>(p);
+        else if (rubix) warp_scalar_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
+        else if (rgba) warp_scalar_kernel<false, true><<<grid, kThreads, 0, st>>>(p);
+        else warp_scalar_kernel<false, false><<<grid, kThreads, 0, st>>>(p);
+        char buf[160];
+        snprintf(buf, sizeof buf, "warp_scalar_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", rubix, rgba, grid.x, grid.y, kThreads);
+        last_kernel_ = buf;
+    }
+    ++launches_;
+    CK(cudaGetLastError());
+    return true;
+}
+
+bool WarpDevice::ensure_slots() {
+    if (!slots_.empty()) return true;
+    const int kSlots = 3;
+    slot_face_bytes_ = static_cast<size_t>(numplates_) * platesize_ * platesize_;
+    slot_out_bytes_ = round_up(npix_, 16);
+    for (int i = 0; i < kSlots; ++i) {
+        Slot *s = new Slot();
+        slots_.push_back(s);
+        CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+        CK(cudaMalloc(&s->d_faces, slot_face_bytes_));
+        CK(cudaMemset(s->d_faces, 0, slot_face_bytes_));
+        CK(cudaMalloc(&s->d_out, slot_out_bytes_));
+        CK(cudaMallocHost(&s->h_faces, slot_face_bytes_));
+        CK(cudaMallocHost(&s->h_out, slot_out_bytes_));
+    }
+    return true;
+}
+
+void WarpDevice::finalize_slot(Slot &s) {
+    if (!s.busy) return;
+    cudaEventSynchronize(s.done);
+    s.busy = false;
+    if (s.direct) return;  // the copy engine already wrote the caller's buffer
+    const int W = width_, H = height_;
+    uint8_t *dst = s.dst + static_cast<size_t>(s.y0) * s.dst_rowbytes + s.x0;
+    if (s.keep_unmapped) {
+        // only mapped pixels are written, like `if (*lmap)` in render_lensmap (:2413)
+        for (int y = 0; y < H; ++y) {
+            const uint8_t *src = s.h_out + static_cast<size_t>(y) * W;
+            uint8_t *row = dst + static_cast<size_t>(y) * s.dst_rowbytes;
+            for (int32_t k = span_off_[static_cast<size_t>(y)]; k < span_off_[static_cast<size_t>(y) + 1]; ++k) {
+                const int32_t a = spans_[static_cast<size_t>(k) * 2], b = spans_[static_cast<size_t>(k) * 2 + 1];
+                memcpy(row + a, src + a, static_cast<size_t>(b - a));
+            }
+        }
+    } else if (s.dst_rowbytes == W) {
+        memcpy(dst, s.h_out, static_cast<size_t>(W) * H);
+    } else {
+        for (int y = 0; y < H; ++y) memcpy(dst + static_cast<size_t>(y) * s.dst_rowbytes, s.h_out + static_cast<size_t>(y) * W, static_cast<size_t>(W));
+    }
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_t *dst_host, size_t dst_frame_stride,
+                           int dst_rowbytes, int x0, int y0, int nframes, bool keep_unmapped) {
+    if (!have_lensmap_) {
+        err_ = "warp_host: no lensmap on the device (call blinky_build_lensmap)";
+        return false;
+    }
+    CK(cudaSetDevice(device_));
+    if (!ensure_slots()) return false;
+    const size_t ps2 = static_cast<size_t>(platesize_) * platesize_;
+    const bool src_pinned = is_pinned(faces_host);
+    const bool dst_pinned = is_pinned(dst_host);
+    const int W = width_, H = height_;
+    bool ok = true;
+    for (int f = 0; f < nframes && ok; ++f) {
+        Slot &s = *slots_[static_cast<size_t>(f) % slots_.size()];
+        finalize_slot(s);  // frees the slot (waits for frame f-3)
+        const uint8_t *src = faces_host + static_cast<size_t>(f) * face_stride;
+        // only plates the lens actually looks at are uploaded (display flags, :764-766)
+        for (int pl = 0; pl < numplates_; ++pl) {
+            if (!display_[pl]) continue;
+            const uint8_t *from = src + pl * ps2;
+            if (!src_pinned) {
+                memcpy(s.h_faces + pl * ps2, from, ps2);
+                from = s.h_faces + pl * ps2;
+            }
+            cudaError_t e = cudaMemcpyAsync(s.d_faces + pl * ps2, from, ps2, cudaMemcpyHostToDevice, s.stream);
+            if (e != cudaSuccess) { ok = fail("cudaMemcpyAsync(H2D faces)", e); break; }
+        }
+        if (!ok) break;
+        if (!warp(s.d_faces, slot_face_bytes_, s.d_out, slot_out_bytes_, 1, s.stream, false)) { ok = false; break; }
+        s.dst = dst_host + static_cast<size_t>(f) * dst_frame_stride;
+        s.dst_rowbytes = dst_rowbytes;
+        s.x0 = x0;
+        s.y0 = y0;
+        s.keep_unmapped = keep_unmapped;
+        s.direct = dst_pinned && !keep_unmapped;
+        cudaError_t e;
+        if (s.direct) {
+            e = cudaMemcpy2DAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, static_cast<size_t>(dst_rowbytes), s.d_out,
+                                  static_cast<size_t>(W), static_cast<size_t>(W), static_cast<size_t>(H), cudaMemcpyDeviceToHost, s.stream);
+        } else {
+            e = cudaMemcpyAsync(s.h_out, s.d_out, static_cast<size_t>(W) * H, cudaMemcpyDeviceToHost, s.stream);
+        }
+        if (e != cudaSuccess) { ok = fail("cudaMemcpyAsync(D2H frame)", e); break; }
+        e = cudaEventRecord(s.done, s.stream);
+        if (e != cudaSuccess) { ok = fail("cudaEventRecord", e); break; }
+        s.busy = true;
+    }
+    // drain in submission order
+    for (size_t k = 0; k < slots_.size(); ++k) {
+        Slot &s = *slots_[(static_cast<size_t>(nframes) + k) % slots_.size()];
+        finalize_slot(s);
+    }
+    if (ok) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) ok = fail("warp_host", e);
+    }
+    return ok;
+}
+
+bool WarpDevice::alloc_pinned(size_t bytes, void **out) {
+    CK(cudaSetDevice(device_));
+    CK(cudaMallocHost(out, bytes));
+    return true;
+}
+
+bool WarpDevice::free_pinned(void *p) {
+    CK(cudaFreeHost(p));
+    return true;
+}
+
+bool WarpDevice::sync() {
+    CK(cudaSetDevice(device_));
+    CK(cudaDeviceSynchronize());
+    return true;
+}
+
+}  // namespace blinky

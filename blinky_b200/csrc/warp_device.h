@@ -1,0 +1,91 @@
+// Device side of the B200 lens-warp path: resident lensmap / LUTs, the warp
+// kernels and the host<->device frame pipeline.  CUDA types are kept out of
+// this header so that plain C++ translation units can include it.
+//
+// Replaces the reference's per-frame hot loop, render_lensmap()
+// (/root/reference/engine/NQ/fisheye.c:2406-2424).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace blinky {
+
+struct TileInfo;  // defined in warp_device.cu
+
+struct LensmapUpload {
+    int width = 0, height = 0, platesize = 0, numplates = 0;
+    const uint32_t *packed = nullptr;        // [height*width]
+    const uint8_t *palmaps = nullptr;        // [6*256]
+    int display[6] = {0, 0, 0, 0, 0, 0};
+    bool rubix = false;
+    const int32_t *span_off = nullptr;       // [height+1]
+    const int32_t *spans = nullptr;          // pairs
+    size_t nspans = 0;
+};
+
+class WarpDevice {
+public:
+    // throws std::runtime_error on CUDA failure
+    explicit WarpDevice(int device);
+    ~WarpDevice();
+
+    int device() const { return device_; }
+    const std::string &last_error() const { return err_; }
+
+    bool upload_lensmap(const LensmapUpload &lm);
+    void set_rubix(bool on) { rubix_ = on; }
+    bool set_background(const uint8_t *bg_host);   // [H][W] or nullptr -> zeros
+    bool set_rgba_table(const uint32_t table[256]);
+    void set_kernel(int variant) { variant_ = variant; }
+
+    // device-resident batch (asynchronous on `stream`, nullptr = own stream)
+    bool warp(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+              bool rgba);
+    // end to end from host buffers (synchronous)
+    bool warp_host(const uint8_t *faces_host, size_t face_stride, uint8_t *dst_host, size_t dst_frame_stride,
+                   int dst_rowbytes, int x0, int y0, int nframes, bool keep_unmapped);
+
+    bool alloc_pinned(size_t bytes, void **out);
+    bool free_pinned(void *p);
+    bool sync();
+
+    int64_t launches() const { return launches_; }
+    const std::string &last_kernel() const { return last_kernel_; }
+
+private:
+    struct Slot;
+    bool ensure_slots();
+    bool fail(const char *what, int cuda_err);
+    void finalize_slot(Slot &s);
+
+    int device_ = 0;
+    int sm_count_ = 148;
+    void *stream_ = nullptr;  // cudaStream_t
+    std::string err_;
+
+    // resident lensmap
+    int width_ = 0, height_ = 0, platesize_ = 0, numplates_ = 0;
+    size_t npix_ = 0, npix_pad_ = 0;
+    int display_[6] = {0, 0, 0, 0, 0, 0};
+    bool rubix_ = false;
+    bool have_lensmap_ = false;
+    uint32_t *d_lensmap_ = nullptr;
+    uint8_t *d_lut_ = nullptr;
+    uint8_t *d_bg_ = nullptr;
+    uint32_t *d_rgba_ = nullptr;
+    bool have_rgba_ = false;
+    std::vector<int32_t> span_off_, spans_;
+    int variant_ = 0;
+
+    // e2e pipeline
+    std::vector<Slot *> slots_;
+    size_t slot_face_bytes_ = 0, slot_out_bytes_ = 0;
+
+    int64_t launches_ = 0;
+    std::string last_kernel_;
+};
+
+}  // namespace blinky

@@ -1,0 +1,209 @@
+/* blinky_b200 — C ABI of the B200-native Blinky lens-warp path.
+ *
+ * This is the thin boundary a C host (TyrQuake's fisheye seams, or a headless
+ * harness) calls into.  It replaces, for the lens-warp path only, what the
+ * reference keeps inside one statically linked translation unit,
+ * /root/reference/engine/NQ/fisheye.c (public surface: engine/include/fisheye.h:4-9).
+ * Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Mapping to the reference (file:line are in /root/reference/engine/NQ/fisheye.c):
+ *
+ *   blinky_create / blinky_destroy      F_Init :642-676 / F_Shutdown :678-681 (state + Lua VM)
+ *   blinky_set_palette                  create_palmap :857-908 (from host_basepal)
+ *   blinky_command                      the console commands registered at :651-665
+ *                                       (fisheye, f_lens, f_globe, f_fov, f_vfov, f_cover,
+ *                                        f_contain, f_rubix, f_rubixgrid, f_help)
+ *   blinky_load_lens[_source]           cmd_lens :1061-1103 / LUA_load_lens :1659-1750
+ *   blinky_load_globe[_source]          cmd_globe :1138-1161 / LUA_load_globe :1752-1875
+ *   blinky_set_zoom                     cmd_fov/vfov/cover/contain :955-965, :1032-1058
+ *   blinky_set_rubix / _rubixgrid       cmd_rubix :933-937 / cmd_rubixgrid :939-953
+ *   blinky_build_lensmap                the rebuild branch of F_RenderView :730-743 ->
+ *                                       create_lensmap :2367-2397 (inverse :2084-2124,
+ *                                       forward :2126-2338), one shot instead of time-sliced
+ *   blinky_warp_*                       render_lensmap :2406-2424 (THE hot loop) on the GPU
+ *   blinky_write_config                 F_WriteConfig :683-696
+ *
+ * Conventions: every function returns BLINKY_OK (0) or a negative BLINKY_E_*
+ * code; blinky_last_error() has the message.  Nothing ever calls exit() (the
+ * reference does on OOM, :723-726).  A context is single-threaded: calls on
+ * one context must be serialised by the caller; use one context per GPU.
+ */
+#ifndef BLINKY_B200_H
+#define BLINKY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLINKY_MAX_PLATES 6 /* MAX_PLATES, fisheye.c:352 */
+
+enum {
+    BLINKY_OK = 0,
+    BLINKY_E_INVALID = -1,   /* bad argument / call order */
+    BLINKY_E_SCRIPT = -2,    /* lens or globe script failed to load or run */
+    BLINKY_E_ZOOM = -3,      /* calc_zoom failed (fisheye.c:1293-1386) */
+    BLINKY_E_NODEVICE = -4,  /* context has no GPU (created with device < 0) */
+    BLINKY_E_CUDA = -5,      /* CUDA runtime error */
+    BLINKY_E_NOMEM = -6,
+    BLINKY_E_STATE = -7      /* lens/globe invalid or lensmap not built */
+};
+
+/* zoom.type, fisheye.c:457 */
+enum { BLINKY_ZOOM_NONE = 0, BLINKY_ZOOM_FOV = 1, BLINKY_ZOOM_VFOV = 2, BLINKY_ZOOM_COVER = 3, BLINKY_ZOOM_CONTAIN = 4 };
+/* lens.map_type, fisheye.c:391 */
+enum { BLINKY_MAP_NONE = 0, BLINKY_MAP_INVERSE = 1, BLINKY_MAP_FORWARD = 2 };
+
+/* Packed device lensmap entry (one per screen pixel, 4 bytes):
+ *   bit 31      valid (reference: lens.pixels[i] != NULL)
+ *   bits 28-30  rubix tint index 0..5, or 7 = none (reference: pixel_tints[i], 255 = none)
+ *   bits 0-27   texel offset into the globe: plate*ps*ps + py*ps + px (GLOBEPIXEL, :349) */
+#define BLINKY_LM_VALID 0x80000000u
+#define BLINKY_LM_TINT_SHIFT 28
+#define BLINKY_LM_TINT_NONE 7u
+#define BLINKY_LM_INDEX_MASK 0x0FFFFFFFu
+
+/* kernel variants (blinky_set_kernel) */
+enum {
+    BLINKY_KERNEL_AUTO = 0,    /* pick per lensmap from the tile classification */
+    BLINKY_KERNEL_GATHER = 1,  /* direct global gather, vectorised coalesced stores */
+    BLINKY_KERNEL_TMA = 2,     /* TMA-staged face tiles in shared memory where tiles are coherent */
+    BLINKY_KERNEL_COMPACT = 3  /* warp-shuffle compaction of scattered face reads */
+};
+
+typedef struct blinky_ctx blinky_ctx;
+typedef void (*blinky_print_fn)(const char *text, void *user);   /* Con_Printf sink */
+typedef void (*blinky_exec_fn)(const char *command, void *user); /* Cmd_ExecuteString hook for `onload` */
+
+/* ---- lifecycle --------------------------------------------------------- */
+/* device >= 0: CUDA device ordinal.  device < 0: host-only context (lensmap
+ * build, palette, console surface work; every blinky_warp_* call fails with
+ * BLINKY_E_NODEVICE — there is no CPU fallback for the hot path). */
+int blinky_create(int device, blinky_ctx **out);
+void blinky_destroy(blinky_ctx *ctx);
+const char *blinky_last_error(blinky_ctx *ctx);
+const char *blinky_version(void);
+
+/* messages the reference sends to Con_Printf; default sink keeps them in a log */
+void blinky_set_print_callback(blinky_ctx *ctx, blinky_print_fn fn, void *user);
+/* where a lens script's `onload` command goes (fisheye.c:1087-1095); default:
+ * this library's own blinky_command */
+void blinky_set_exec_callback(blinky_ctx *ctx, blinky_exec_fn fn, void *user);
+const char *blinky_log(blinky_ctx *ctx);
+void blinky_log_clear(blinky_ctx *ctx);
+
+/* ---- configuration (host side) ----------------------------------------- */
+/* directory that contains lua-scripts/{globes,lenses}/ (com_basedir, :1666) */
+int blinky_set_basedir(blinky_ctx *ctx, const char *basedir);
+/* host_basepal: 256 RGB triplets -> six rubix tint LUTs */
+int blinky_set_palette(blinky_ctx *ctx, const uint8_t palette[768]);
+/* executes one console command line, e.g. "f_lens panini", "f_fov 170",
+ * "f_globe cube", "f_rubix", "f_rubixgrid 10 4 1", "f_cover", "fisheye 1" */
+int blinky_command(blinky_ctx *ctx, const char *text);
+
+int blinky_load_globe(blinky_ctx *ctx, const char *name);
+int blinky_load_lens(blinky_ctx *ctx, const char *name);
+/* same, from source text instead of <basedir>/lua-scripts/...; the text is
+ * kept and re-run on every rebuild exactly like the file would be (:737) */
+int blinky_load_globe_source(blinky_ctx *ctx, const char *name, const char *lua_source);
+int blinky_load_lens_source(blinky_ctx *ctx, const char *name, const char *lua_source);
+int blinky_set_zoom(blinky_ctx *ctx, int zoom_type, int fov_degrees);
+int blinky_set_rubix(blinky_ctx *ctx, int enabled);
+int blinky_set_rubixgrid(blinky_ctx *ctx, int numcells, double cell_size, double pad_size);
+
+/* ---- lensmap build ("InitLensMap") -------------------------------------- */
+/* Builds the lensmap for a width x height view and square plates of
+ * `platesize` pixels (the reference forces platesize = min(w,h), :707; pass
+ * platesize <= 0 for that behaviour).  threads <= 1 evaluates the lens in the
+ * reference's own order on one Lua state; threads > 1 splits rows over cloned
+ * Lua states (requires lens_inverse to be a pure function of x,y — true for
+ * every shipped lens).  On a GPU context the packed map, tile table and tint
+ * LUTs are uploaded too. */
+int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, int threads);
+/* 1 if a lens/globe/zoom/rubixgrid/size change since the last build requires a rebuild (:730) */
+int blinky_needs_rebuild(blinky_ctx *ctx, int width, int height, int platesize);
+
+/* ---- state queries ------------------------------------------------------ */
+int blinky_fisheye_enabled(blinky_ctx *ctx);          /* fisheye_enabled, :293 */
+int blinky_lens_valid(blinky_ctx *ctx);
+int blinky_globe_valid(blinky_ctx *ctx);
+const char *blinky_lens_name(blinky_ctx *ctx);
+const char *blinky_globe_name(blinky_ctx *ctx);
+const char *blinky_lens_onload(blinky_ctx *ctx);      /* "" when nil */
+int blinky_map_type(blinky_ctx *ctx);
+int blinky_zoom_type(blinky_ctx *ctx);
+int blinky_zoom_fov(blinky_ctx *ctx);
+int blinky_max_fov(blinky_ctx *ctx);
+int blinky_max_vfov(blinky_ctx *ctx);
+double blinky_lens_width(blinky_ctx *ctx);
+double blinky_lens_height(blinky_ctx *ctx);
+double blinky_scale(blinky_ctx *ctx);                 /* lens.scale after a build */
+int blinky_rubix_enabled(blinky_ctx *ctx);
+int blinky_numplates(blinky_ctx *ctx);
+int blinky_platesize(blinky_ctx *ctx);
+int blinky_width(blinky_ctx *ctx);
+int blinky_height(blinky_ctx *ctx);
+/* per plate: forward[3] right[3] up[3] fov dist as 11 floats; returns numplates */
+int blinky_get_plates(blinky_ctx *ctx, float *out, int max_plates);
+/* globe.plates[i].display after a build (:1976): which plates the lens uses */
+int blinky_get_display(blinky_ctx *ctx, int out[BLINKY_MAX_PLATES]);
+double blinky_plate_fov(blinky_ctx *ctx, int plate);  /* radians: fisheye_plate_fov source, :769 */
+/* six 256-entry tint LUTs (globe.plates[i].palette) */
+int blinky_get_palmaps(blinky_ctx *ctx, uint8_t out[BLINKY_MAX_PLATES * 256]);
+/* lensmap in the reference's terms: idx = pointer - globe.pixels or -1; tint 0..5 or 255 */
+int blinky_get_lensmap(blinky_ctx *ctx, int32_t *idx, uint8_t *tint);
+/* the packed 32-bit entries the kernels read */
+int blinky_get_lensmap_packed(blinky_ctx *ctx, uint32_t *out);
+int64_t blinky_mapped_pixels(blinky_ctx *ctx);        /* M in the 5*W*H + M byte count */
+/* direct script probes (LUAtoC_lens_inverse/_forward before float narrowing):
+ * return 1 = values, 0 = nil, negative = error */
+int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]);
+int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y);
+/* F_WriteConfig text; returns bytes needed (excluding NUL) */
+int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize);
+
+/* ---- hot path ("RenderLensMap") — GPU only ------------------------------- */
+int blinky_set_kernel(blinky_ctx *ctx, int kernel_variant);
+/* Frame shown where the lens maps nothing (what Draw_TileClear left in
+ * vid.buffer, :802).  [height][width] bytes, NULL = all zero.  Uploaded once. */
+int blinky_set_background(blinky_ctx *ctx, const uint8_t *background_host);
+
+/* Device-resident batch: d_faces -> d_out on `stream` (a cudaStream_t, may be
+ * NULL for the context's own stream).  d_faces: nframes x [numplates][ps][ps]
+ * bytes, frame stride face_stride bytes; d_out: nframes x [height][width]
+ * bytes, stride out_stride.  Asynchronous.  One kernel launch per call. */
+int blinky_warp_device(blinky_ctx *ctx, const void *d_faces, size_t face_stride, void *d_out, size_t out_stride,
+                       int nframes, void *stream);
+
+/* End to end from HOST buffers: pinned-staged cudaMemcpyAsync of each frame's
+ * displayed plates, the warp, and the copy back, software-pipelined over
+ * internal streams.  faces_host: nframes x [numplates][ps][ps].  dst_host: nframes
+ * screens of dst_rowbytes pitch; the view rectangle starts at (x0,y0) inside
+ * each (scr_vrect, VBUFFER macro :634).  If keep_unmapped != 0 only mapped
+ * pixels are written into dst (exact reference semantics, :2413); otherwise
+ * unmapped pixels receive the background set above.  Synchronous. */
+int blinky_warp_host(blinky_ctx *ctx, const uint8_t *faces_host, size_t face_stride, uint8_t *dst_host,
+                     size_t dst_frame_stride, int dst_rowbytes, int x0, int y0, int nframes, int keep_unmapped);
+
+/* pinned host memory helpers for callers that want zero staging copies */
+int blinky_alloc_pinned(blinky_ctx *ctx, size_t bytes, void **out);
+int blinky_free_pinned(blinky_ctx *ctx, void *ptr);
+int blinky_sync(blinky_ctx *ctx);
+
+/* Fused 8-bit -> 32-bit palette expansion (engine/common/vid_sdl.c:539-546,
+ * d_8to24table): same warp, output one uint32 per pixel.  table: 256 entries. */
+int blinky_set_rgba_table(blinky_ctx *ctx, const uint32_t table[256]);
+int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_stride, void *d_out_rgba,
+                            size_t out_stride, int nframes, void *stream);
+
+/* number of kernel launches issued by this context so far */
+int64_t blinky_launch_count(blinky_ctx *ctx);
+/* last warp kernel's name and launch geometry, for reports */
+const char *blinky_last_kernel(blinky_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLINKY_B200_H */
