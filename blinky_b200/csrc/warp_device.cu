@@ -311,7 +311,9 @@ bool WarpDevice::warp(const void *d_faces, size_t face_stride, void *d_out, size
         err_ = "warp: at most 65535 frames per launch";
         return false;
     }
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(stream_);
+    // NULL is CUDA's default stream (what torch.cuda.current_stream() hands out
+    // unless the caller made its own) — NOT this context's private stream.
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     WarpParams p;
     p.lensmap4 = reinterpret_cast<const uint4 *>(d_lensmap_);
     p.faces = static_cast<const uint8_t *>(d_faces);

@@ -41,7 +41,7 @@ public:
     bool set_rgba_table(const uint32_t table[256]);
     void set_kernel(int variant) { variant_ = variant; }
 
-    // device-resident batch (asynchronous on `stream`, nullptr = own stream)
+    // device-resident batch (asynchronous on `stream`, nullptr = CUDA default stream)
     bool warp(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
               bool rgba);
     // end to end from host buffers (synchronous)

@@ -170,8 +170,8 @@ int blinky_set_kernel(blinky_ctx *ctx, int kernel_variant);
  * vid.buffer, :802).  [height][width] bytes, NULL = all zero.  Uploaded once. */
 int blinky_set_background(blinky_ctx *ctx, const uint8_t *background_host);
 
-/* Device-resident batch: d_faces -> d_out on `stream` (a cudaStream_t, may be
- * NULL for the context's own stream).  d_faces: nframes x [numplates][ps][ps]
+/* Device-resident batch: d_faces -> d_out on `stream` (a cudaStream_t; NULL is
+ * CUDA's default stream).  d_faces: nframes x [numplates][ps][ps]
  * bytes, frame stride face_stride bytes; d_out: nframes x [height][width]
  * bytes, stride out_stride.  Asynchronous.  One kernel launch per call. */
 int blinky_warp_device(blinky_ctx *ctx, const void *d_faces, size_t face_stride, void *d_out, size_t out_stride,

@@ -1,0 +1,214 @@
+"""The Lua-subset evaluator (blinky_b200/csrc/minilua) exercised like a `lua` binary.
+Expected values follow the Lua 5.2 reference manual."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "blinky_b200", "csrc", "minilua", "minilua")
+
+
+@pytest.fixture(scope="module")
+def lua(bb):
+    if not os.path.exists(EXE):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.check_call(["make", "minilua"], cwd=os.path.join(ROOT, "blinky_b200"), env=env)
+
+    def run(code: str):
+        r = subprocess.run([EXE, "-e", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+        return r.returncode, r.stdout, r.stderr
+
+    return run
+
+
+def ok(lua, code, expect_out=None):
+    rc, out, err = lua(code)
+    assert rc == 0, err
+    if expect_out is not None:
+        assert out == expect_out
+    return out
+
+
+def test_assignment_and_multiple_returns(lua):
+    ok(lua, """
+local a, b, c = 1, 2
+assert(a == 1 and b == 2 and c == nil)
+local function f(...) return ... end
+assert(select('#', f(1,2,3)) == 3)
+local t = {f(1,2,3), f(4,5,6)}
+assert(#t == 4 and t[1]==1 and t[2]==4 and t[3]==5 and t[4]==6)
+assert(select('#', (f(1,2,3))) == 1)
+local x, y = 1, 2
+x, y = y, x
+assert(x == 2 and y == 1)
+local function two() return 1, 2 end
+local p, q, r = two()
+assert(p == 1 and q == 2 and r == nil)
+local m = math.max(two())
+assert(m == 2)
+""")
+
+
+def test_closures_and_scoping(lua):
+    ok(lua, """
+local function counter() local n = 0; return function() n = n + 1; return n end end
+local c1, c2 = counter(), counter()
+assert(c1()==1 and c1()==2 and c2()==1)
+local fs = {}
+for i=1,3 do fs[i] = function() return i end end
+assert(fs[1]()==1 and fs[2]()==2 and fs[3]()==3)
+local v = 1
+do local v = 2; assert(v == 2) end
+assert(v == 1)
+local w = 1
+local w = w + 1
+assert(w == 2)
+local function fib(n) if n < 2 then return n end return fib(n-1)+fib(n-2) end
+assert(fib(20) == 6765)
+-- a global defined later is visible at call time
+function g1() return g2() + 1 end
+function g2() return 41 end
+assert(g1() == 42)
+-- repeat..until sees the body's locals
+local i = 0
+repeat local k = i; i = i + 1 until k >= 4
+assert(i == 5)
+""")
+
+
+def test_loops(lua):
+    ok(lua, """
+local s = 0
+for x=1,2,0.25 do s = s + x end
+assert(s == 7.5)
+for x=10,1,-3 do s = s + 1 end
+assert(s == 11.5)
+for x=1,0 do error('never') end
+local i = 0
+while true do i = i + 1; if i > 10 then break end end
+assert(i == 11)
+local sum = 0
+for k,v in ipairs({10,20,30}) do sum = sum + k*v end
+assert(sum == 140)
+local cnt = 0
+for k,v in pairs({a=1,b=2,3}) do cnt = cnt + 1 end
+assert(cnt == 3)
+""")
+
+
+def test_arithmetic_follows_ieee_and_lua(lua):
+    ok(lua, """
+assert(2^10 == 1024 and 7 % 3 == 1 and -7 % 3 == 2 and 7 % -3 == -2)
+assert(2^-1 == 0.5 and -2^2 == -4 and 2^3^2 == 512)
+assert(1 .. 2 == "12" and "10" + 5 == 15 and "0x10" + 0 == 16)
+assert(.25 == 0.25 and 1.e-10 == 1e-10 and 0x10 == 16 and 3 == 3.0)
+local nan = 0/0
+assert(nan ~= nan and not (nan < 0) and not (nan >= 0))
+assert(1/0 == math.huge and -1/0 == -math.huge)
+assert(tostring(1/0) == "inf" and tostring(10/2) == "5" and tostring(0.1) == "0.1")
+assert(tostring(2^53) == "9.007199254741e+15")
+assert(0.1 + 0.2 ~= 0.3)
+assert(19.73920880217871723738 == 19.739208802178716)
+assert(math.pi == 3.14159265358979323846)
+local ip, fp = math.modf(3.75); assert(ip == 3 and fp == 0.75)
+ip, fp = math.modf(-3.75); assert(ip == -3 and fp == -0.75)
+assert(math.floor(-0.5) == -1 and math.ceil(-0.5) == 0 and math.abs(-3) == 3)
+assert(math.fmod(7, 3) == 1 and math.fmod(-7, 3) == -1)
+assert(math.sqrt(2)*math.sqrt(2) ~= 2)
+""")
+
+
+def test_logic_and_comparison(lua):
+    ok(lua, """
+assert(not nil == true and (nil or 5) == 5 and (false and 1) == false and (1 and 2) == 2)
+assert(1 < 2 and "a" < "b" and 2 >= 2 and not (1 == "1"))
+assert(nil == nil and nil ~= false)
+local t = {}
+assert(t == t and {} ~= {})
+""")
+
+
+def test_tables(lua):
+    ok(lua, """
+local cols = {3,3}
+local r = math.modf(0.5)
+assert(cols[r+1] == 3)            -- float key 1.0 hits the array part
+local t = {}
+t[1.0] = "x"; t[2] = "y"
+assert(#t == 2 and t[1] == "x")
+t = {1,2,3,nil}
+assert(#t == 3)
+t = {n=1, [2]="b", "a"}
+assert(t.n == 1 and t[1] == "a" and t[2] == "b" and #t == 2)
+t = {{1,2},{3,4},}
+assert(t[2][1] == 3)
+t = {}
+t[3] = 'c'; t[2] = 'b'; t[1] = 'a'
+assert(#t == 3)
+assert(math.max(table.unpack({3,9,2})) == 9)
+table.insert(t, 'd'); assert(#t == 4 and t[4] == 'd')
+assert(table.remove(t) == 'd' and #t == 3)
+assert(table.concat({1,2,3}, ",") == "1,2,3")
+""")
+
+
+def test_strings(lua):
+    ok(lua, """
+assert(("abc"):len() == 3 and ("abc"):upper() == "ABC" and #"abc" == 3)
+assert(string.format("%d %5.2f %s %g", 3, 1.5, "z", 0.1) == "3  1.50 z 0.1")
+assert(string.sub("hello", 2, 4) == "ell" and string.rep("ab", 3) == "ababab")
+local ls = [[
+hello]]
+assert(ls == "hello")
+assert("a\\n" == "a\\10" and '\\65' == "A" and "\\x41" == "A")
+--[[ multi
+line ]] assert(true)
+--[==[ another ]==]
+assert(tonumber("12") == 12 and tonumber("z") == nil and tonumber("ff", 16) == 255)
+""")
+
+
+def test_errors_are_caught_and_positioned(lua):
+    out = ok(lua, """
+local ok, err = pcall(function() local z = nil; return z + 1 end)
+assert(not ok)
+print(err)
+ok, err = pcall(function() error("boom") end)
+print(ok, err)
+ok, err = pcall(function() local t = nil; return t.x end)
+print(err)
+ok, err = pcall(function() undefined_function() end)
+print(err)
+""")
+    lines = out.strip().split("\n")
+    assert "attempt to perform arithmetic on a nil value" in lines[0] and ":2:" in lines[0]
+    assert lines[1].startswith("false") and "boom" in lines[1]
+    assert "attempt to index" in lines[2]
+    assert "attempt to call" in lines[3] and "undefined_function" in lines[3]
+
+
+def test_syntax_errors_fail_to_load(lua):
+    rc, out, err = lua("x = = 1")
+    assert rc != 0 and "unexpected symbol" in err
+    rc, out, err = lua("for i=1,2 do")
+    assert rc != 0 and "'end' expected" in err
+    rc, out, err = lua("goto done")
+    assert rc != 0
+
+
+def test_stack_overflow_is_an_error_not_a_crash(lua):
+    out = ok(lua, "local function f() return 1 + f() end print(pcall(f))")
+    assert out.startswith("false") and "stack overflow" in out
+
+
+def test_cycles_are_collected(lua):
+    # closures that capture themselves form reference cycles; memory must stay bounded
+    ok(lua, """
+for i = 1, 300000 do
+  local function rec(n) if n == 0 then return 0 end return rec(n-1) end
+  rec(1)
+  local t = {}; t.self = t
+end
+print("done")
+""", "done\n")
