@@ -96,6 +96,7 @@ _SIGNATURES = [
     ("blinky_sync", c_int, [_CTX]),
     ("blinky_set_rgba_table", c_int, [_CTX, c_void_p]),
     ("blinky_warp_device_rgba", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
+    ("blinky_plan_summary", c_char_p, [_CTX]),
     ("blinky_launch_count", c_int64, [_CTX]),
     ("blinky_last_kernel", c_char_p, [_CTX]),
 ]
@@ -258,6 +259,7 @@ class Fisheye:
     mapped_pixels = property(lambda s: int(s._lib.blinky_mapped_pixels(s._ctx)))
     launch_count = property(lambda s: int(s._lib.blinky_launch_count(s._ctx)))
     last_kernel = property(lambda s: s._lib.blinky_last_kernel(s._ctx).decode())
+    plan_summary = property(lambda s: s._lib.blinky_plan_summary(s._ctx).decode())
 
     def plates(self) -> np.ndarray:
         out = np.zeros((MAX_PLATES, 11), np.float32)

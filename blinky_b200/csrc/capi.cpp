@@ -2,12 +2,14 @@
 // FisheyeHost (host-side scripts/console/lensmap build) and WarpDevice (CUDA).
 #include "../../include/blinky_b200.h"
 
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
 
 #include "fisheye_host.h"
+#include "tile_plan.h"
 #include "warp_device.h"
 
 using blinky::FisheyeHost;
@@ -45,6 +47,9 @@ bool upload(blinky_ctx *c) {
     lm.span_off = c->host.row_span_offsets().data();
     lm.spans = c->host.row_spans().data();
     lm.nspans = c->host.row_spans().size() / 2;
+    // TMA needs 16-byte aligned plate rows; other plate sizes use direct gathers only
+    blinky::TilePlan plan = blinky::make_tile_plan(lm.packed, lm.width, lm.height, lm.platesize, lm.platesize % 16 == 0);
+    lm.plan = &plan;
     if (!c->dev->upload_lensmap(lm)) {
         c->err = c->dev->last_error();
         return false;
@@ -302,6 +307,18 @@ int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_st
 }
 
 int64_t blinky_launch_count(blinky_ctx *ctx) { return ctx->dev ? ctx->dev->launches() : 0; }
+const char *blinky_plan_summary(blinky_ctx *ctx) {
+    if (!ctx->host.built()) return "";
+    blinky::TilePlan pl = blinky::make_tile_plan(ctx->host.packed().data(), ctx->host.width(), ctx->host.height(),
+                                                 ctx->host.platesize(), ctx->host.platesize() % 16 == 0);
+    const double npix = static_cast<double>(ctx->host.width()) * ctx->host.height();
+    char buf[256];
+    snprintf(buf, sizeof buf, "tiles %dx%d of %dx%d px: %d box (TMA, %.3f B/px staged, %zu shapes), %d gather, %d empty; entries %.3f B/px",
+             pl.tiles_x, pl.tiles_y, blinky::kTileW, blinky::kTileH, pl.n_box, static_cast<double>(pl.box_bytes) / npix,
+             pl.shapes.size(), pl.n_gather, pl.n_empty, static_cast<double>(pl.entries.size()) / npix);
+    ctx->scratch = buf;
+    return ctx->scratch.c_str();
+}
 const char *blinky_last_kernel(blinky_ctx *ctx) { return ctx->dev ? ctx->dev->last_kernel().c_str() : ""; }
 
 }  // extern "C"

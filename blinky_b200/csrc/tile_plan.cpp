@@ -1,0 +1,112 @@
+#include "tile_plan.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/blinky_b200.h"
+
+namespace blinky {
+
+TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box) {
+    TilePlan plan;
+    plan.width = width;
+    plan.height = height;
+    plan.platesize = platesize;
+    plan.tiles_x = (width + kTileW - 1) / kTileW;
+    plan.tiles_y = (height + kTileH - 1) / kTileH;
+    plan.tiles.reserve(static_cast<size_t>(plan.tiles_x) * plan.tiles_y);
+    const uint32_t ps = static_cast<uint32_t>(platesize);
+    const uint32_t ps2 = ps * ps;
+    std::vector<uint32_t> tile(kTilePixels);
+
+    for (int ty = 0; ty < plan.tiles_y; ++ty) {
+        for (int tx = 0; tx < plan.tiles_x; ++tx) {
+            const int x0 = tx * kTileW, y0 = ty * kTileH;
+            // collect the tile (pixels beyond the frame edge are unmapped)
+            bool any = false, one_plate = true;
+            uint32_t plate = 0;
+            uint32_t minx = ~0u, miny = ~0u, maxx = 0, maxy = 0;
+            for (int r = 0; r < kTileH; ++r) {
+                for (int c = 0; c < kTileW; ++c) {
+                    uint32_t e = 0;
+                    if (y0 + r < height && x0 + c < width) e = packed[static_cast<size_t>(y0 + r) * width + x0 + c];
+                    tile[static_cast<size_t>(r) * kTileW + c] = e;
+                    if (!(e & BLINKY_LM_VALID)) continue;
+                    const uint32_t idx = e & BLINKY_LM_INDEX_MASK;
+                    const uint32_t p = idx / ps2, rem = idx % ps2;
+                    const uint32_t py = rem / ps, px = rem % ps;
+                    if (!any) {
+                        any = true;
+                        plate = p;
+                    } else if (p != plate) {
+                        one_plate = false;
+                    }
+                    minx = std::min(minx, px);
+                    maxx = std::max(maxx, px);
+                    miny = std::min(miny, py);
+                    maxy = std::max(maxy, py);
+                }
+            }
+            TileDesc d;
+            memset(&d, 0, sizeof d);
+            d.px = static_cast<uint16_t>(x0);
+            d.py = static_cast<uint16_t>(y0);
+            if (!any) {
+                d.type = TILE_EMPTY;
+                ++plan.n_empty;
+                plan.tiles.push_back(d);
+                continue;
+            }
+            bool box = allow_box && one_plate;
+            uint32_t bw = 0, bh = 0;
+            if (box) {
+                // TMA faults ("illegal instruction") unless the innermost coordinate is a
+                // multiple of 16 bytes (measured on B200, scripts/tma_probe.cu): start the
+                // box on a 16-texel boundary.  The row coordinate is unconstrained.
+                minx &= ~15u;
+                bw = ((maxx - minx + 1) + 15) / 16 * 16;
+                bh = ((maxy - miny + 1) + 7) / 8 * 8;
+                if (bw > 128 || bh > 256 || bw * bh > static_cast<uint32_t>(kMaxBoxBytes)) box = false;
+            }
+            // entry blocks start 16-byte aligned
+            plan.entries.resize((plan.entries.size() + 15) / 16 * 16);
+            d.entry_offset = static_cast<uint32_t>(plan.entries.size());
+            if (box) {
+                d.type = TILE_BOX;
+                d.plate = static_cast<uint8_t>(plate);
+                d.box_x = static_cast<int16_t>(minx);
+                d.box_y = static_cast<int16_t>(miny);
+                d.box_w16 = static_cast<uint8_t>(bw / 16);
+                d.box_h8 = static_cast<uint8_t>(bh / 8);
+                plan.entries.resize(plan.entries.size() + kTilePixels * 2);
+                uint16_t *out = reinterpret_cast<uint16_t *>(plan.entries.data() + d.entry_offset);
+                for (int i = 0; i < kTilePixels; ++i) {
+                    const uint32_t e = tile[static_cast<size_t>(i)];
+                    if (!(e & BLINKY_LM_VALID)) {
+                        out[i] = static_cast<uint16_t>(BLINKY_LM_TINT_NONE << kBoxTintShift);
+                        continue;
+                    }
+                    const uint32_t rem = (e & BLINKY_LM_INDEX_MASK) % ps2;
+                    const uint32_t py = rem / ps, px = rem % ps;
+                    const uint32_t off = (py - miny) * bw + (px - minx);
+                    const uint32_t tint = (e >> BLINKY_LM_TINT_SHIFT) & 7u;
+                    out[i] = static_cast<uint16_t>(kBoxValid | (tint << kBoxTintShift) | off);
+                }
+                const uint16_t shape = static_cast<uint16_t>((d.box_w16 << 8) | d.box_h8);
+                if (std::find(plan.shapes.begin(), plan.shapes.end(), shape) == plan.shapes.end()) plan.shapes.push_back(shape);
+                plan.box_bytes += static_cast<uint64_t>(bw) * bh;
+                ++plan.n_box;
+            } else {
+                d.type = TILE_GATHER;
+                plan.entries.resize(plan.entries.size() + kTilePixels * 4);
+                memcpy(plan.entries.data() + d.entry_offset, tile.data(), kTilePixels * 4);
+                ++plan.n_gather;
+            }
+            plan.tiles.push_back(d);
+        }
+    }
+    plan.entries.resize((plan.entries.size() + 15) / 16 * 16 + 16);
+    return plan;
+}
+
+}  // namespace blinky

@@ -12,13 +12,16 @@
 // sm_100a only.  HBM-bound byte work: no tensor cores on purpose.
 #include "warp_device.h"
 
+#include <cuda.h>  // CUtensorMap types only; the driver entry point is fetched at run time
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
 #include "../../include/blinky_b200.h"
+#include "tile_plan.h"
 
 namespace blinky {
 
@@ -161,6 +164,226 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
     else o[i] = static_cast<uint8_t>(b);
 }
 
+
+// --------------------------------------------------------------------------
+// K2: tiled, warp-specialised kernel with TMA-staged source boxes.
+//
+// Persistent CTAs (1 producer warp + 8 consumer warps) walk work items
+// (tile, frame) in tile-major order through a kStages-deep shared-memory ring.
+//   producer (one lane): waits for a free stage, copies the 16-byte TileDesc into
+//     the stage, and issues (a) one 4-D TMA tensor load (x, y, plate, frame) of the
+//     tile's source box and (b) one bulk copy of the tile's entry block — both
+//     complete on the stage's `full` mbarrier.  It runs up to kStages items ahead,
+//     so every global-memory latency is off the consumers' critical path.
+//   consumers (256 threads, one 4-pixel quad each): wait on `full`, read the
+//     descriptor, their four entries and the four source bytes from SHARED memory,
+//     apply the tint LUT, write one 32-bit word (one 128-bit word in RGBA mode),
+//     then release the stage on its `empty` mbarrier.  No block-wide barrier.
+// GATHER tiles (plate seams, singular points) carry 32-bit entries and read the
+// globe directly, with the same 2-D thread layout (a warp covers 32x4 pixels).
+// --------------------------------------------------------------------------
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = kThreads / 32;          // 8
+constexpr int kTiledThreads = kThreads + 32;           // + producer warp
+constexpr int kTmapRows = 32;  // descriptor table index = (w16-1)*kTmapRows + (h8-1)
+
+struct TiledParams {
+    const TileDesc *tiles;
+    const uint8_t *entries;
+    const CUtensorMap *tmaps;
+    const uint8_t *faces;
+    size_t face_stride;
+    const uint8_t *bg;
+    const uint8_t *lut;
+    const uint32_t *rgba;
+    void *out;
+    size_t out_stride;
+    uint32_t ntiles, nframes, total;
+    int width, height;
+};
+
+struct __align__(128) TiledStage {
+    uint8_t box[kMaxBoxBytes];          // TMA destination (128-byte aligned)
+    uint8_t entries[kTilePixels * 4];   // 2 KB used by BOX tiles, 4 KB by GATHER tiles
+    uint4 desc;                         // TileDesc
+    uint32_t frame;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// NB (measured on B200, scripts/tma_probe.cu): the innermost coordinate must be a
+// multiple of 16 bytes or the TMA unit raises "illegal instruction".
+__device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *tmap, int x, int y, int plate, int frame,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(plate), "r"(frame), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TiledStage *stages = reinterpret_cast<TiledStage *>(smem_raw);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(TiledStage) * kStages);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(empty_bar + kStages);
+    uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + 6 * 256);
+
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (RUBIX) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+        for (int i = tid; i < 6 * 256 / 4; i += kTiledThreads) dst[i] = __ldg(src + i);
+    }
+    if (RGBA) {
+        for (int i = tid; i < 256; i += kTiledThreads) s_rgba[i] = __ldg(p.rgba + i);
+    }
+    __syncthreads();
+
+    const uint32_t G = gridDim.x;
+    if (tid >= kThreads) {
+        // ------------------------------ producer warp ------------------------------
+        if (tid == kThreads) {
+            uint32_t w = blockIdx.x;
+            uint4 next = make_uint4(0, 0, 0, 0);
+            if (w < p.total) next = __ldg(reinterpret_cast<const uint4 *>(p.tiles + w / p.nframes));
+            for (uint32_t it = 0; w < p.total; w += G, ++it) {
+                const uint32_t stage = it % kStages, round = it / kStages;
+                const uint4 d = next;
+                const uint32_t tile = w / p.nframes, frame = w - tile * p.nframes;
+                const uint32_t wn = w + G;
+                if (wn < p.total) next = __ldg(reinterpret_cast<const uint4 *>(p.tiles + wn / p.nframes));
+                if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1u);
+                TiledStage &st = stages[stage];
+                st.desc = d;
+                st.frame = frame;
+                const uint32_t type = (d.z >> 8) & 0xffu;
+                if (type == TILE_BOX) {
+                    const uint32_t w16 = (d.z >> 16) & 0xffu, h8 = d.z >> 24;
+                    const uint32_t box_bytes = w16 * 16u * h8 * 8u;
+                    mbar_expect_tx(&full_bar[stage], box_bytes + kTilePixels * 2);
+                    tma_load_box(st.box, p.tmaps + (w16 - 1) * kTmapRows + (h8 - 1), static_cast<int>(static_cast<int16_t>(d.y & 0xffffu)),
+                                 static_cast<int>(static_cast<int16_t>(d.y >> 16)), static_cast<int>(d.z & 0xffu),
+                                 static_cast<int>(frame), &full_bar[stage]);
+                    bulk_copy_g2s(st.entries, p.entries + d.x, kTilePixels * 2, &full_bar[stage]);
+                } else if (type == TILE_GATHER) {
+                    mbar_expect_tx(&full_bar[stage], kTilePixels * 4);
+                    bulk_copy_g2s(st.entries, p.entries + d.x, kTilePixels * 4, &full_bar[stage]);
+                } else {
+                    mbar_arrive(&full_bar[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // -------------------------------- consumers --------------------------------
+    const uint32_t row = tid >> 3, qx = tid & 7, lane = tid & 31;
+    uint32_t it = 0;
+    for (uint32_t w = blockIdx.x; w < p.total; w += G, ++it) {
+        const uint32_t stage = it % kStages, round = it / kStages;
+        TiledStage &st = stages[stage];
+        mbar_wait(&full_bar[stage], round & 1u);
+        const uint4 d = st.desc;
+        const uint32_t frame = st.frame;
+        const uint32_t type = (d.z >> 8) & 0xffu;
+        const uint32_t x = (d.w & 0xffffu) + qx * 4, y = (d.w >> 16) + row;
+        const bool inside = x < static_cast<uint32_t>(p.width) && y < static_cast<uint32_t>(p.height);
+
+        uint32_t v[4] = {0, 0, 0, 0};
+        uint32_t tint[4] = {7, 7, 7, 7};
+        uint32_t valid = 0;  // bit k: pixel k is mapped
+        if (type == TILE_BOX) {
+            const uint2 e2 = reinterpret_cast<const uint2 *>(st.entries)[tid];
+            const uint32_t ent[4] = {e2.x & 0xffffu, e2.x >> 16, e2.y & 0xffffu, e2.y >> 16};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ent[k] & kBoxValid) {
+                    valid |= 1u << k;
+                    v[k] = st.box[ent[k] & kBoxOffsetMask];
+                    tint[k] = (ent[k] >> kBoxTintShift) & 7u;
+                }
+            }
+        } else if (type == TILE_GATHER) {
+            const uint4 e4 = reinterpret_cast<const uint4 *>(st.entries)[tid];
+            const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(frame) * p.face_stride;
+            const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ent[k] & BLINKY_LM_VALID) {
+                    valid |= 1u << k;
+                    v[k] = ld_face(faces + (ent[k] & BLINKY_LM_INDEX_MASK));
+                    tint[k] = (ent[k] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                }
+            }
+        }
+        // the stage's shared memory has been consumed into registers: hand it back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+
+        if (inside) {
+            const size_t pix = static_cast<size_t>(y) * p.width + x;
+            uint32_t bgw = 0;
+            if (valid != 0xfu) bgw = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
+            uint32_t px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t b = v[k];
+                if (RUBIX) {
+                    if (tint[k] != BLINKY_LM_TINT_NONE) b = s_lut[tint[k] * 256 + b];
+                }
+                if (!((valid >> k) & 1u)) b = (bgw >> (8 * k)) & 0xffu;
+                px[k] = b;
+            }
+            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
+            if (RGBA) {
+                st_stream_v4(reinterpret_cast<uint4 *>(o) + (pix >> 2), make_uint4(s_rgba[px[0]], s_rgba[px[1]], s_rgba[px[2]], s_rgba[px[3]]));
+            } else {
+                st_stream_u32(reinterpret_cast<uint32_t *>(o) + (pix >> 2), px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24));
+            }
+        }
+    }
+}
+
+constexpr size_t kTiledSmemBytes = sizeof(TiledStage) * kStages + 2 * kStages * sizeof(uint64_t) + 6 * 256 + 256 * 4;
+
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
@@ -179,6 +402,18 @@ struct WarpDevice::Slot {
     int dst_rowbytes = 0, x0 = 0, y0 = 0;
     bool keep_unmapped = false, direct = false;
 };
+
+struct WarpDevice::TmapSet {
+    const void *faces = nullptr;
+    size_t face_stride = 0;
+    int nframes = 0;
+    CUtensorMap *d_table = nullptr;  // [8 * kTmapRows]
+    uint64_t last_use = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 #define CK(call)                                      \
     do {                                              \
@@ -233,6 +468,12 @@ WarpDevice::~WarpDevice() {
     cudaFree(d_lut_);
     cudaFree(d_bg_);
     cudaFree(d_rgba_);
+    cudaFree(d_tiles_);
+    cudaFree(d_entries_);
+    for (TmapSet *t : tmap_sets_) {
+        cudaFree(t->d_table);
+        delete t;
+    }
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
 }
 
@@ -267,6 +508,34 @@ bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
     span_off_.assign(lm.span_off, lm.span_off + lm.height + 1);
     spans_.assign(lm.spans, lm.spans + lm.nspans * 2);
     have_lensmap_ = true;
+    // tiled layout
+    have_plan_ = false;
+    plan_has_box_ = false;
+    cudaFree(d_tiles_);
+    cudaFree(d_entries_);
+    d_tiles_ = nullptr;
+    d_entries_ = nullptr;
+    for (TmapSet *t : tmap_sets_) {
+        cudaFree(t->d_table);
+        delete t;
+    }
+    tmap_sets_.clear();
+    if (lm.plan && !lm.plan->tiles.empty()) {
+        const TilePlan &pl = *lm.plan;
+        CK(cudaMalloc(&d_tiles_, pl.tiles.size() * sizeof(TileDesc)));
+        CK(cudaMemcpy(d_tiles_, pl.tiles.data(), pl.tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&d_entries_, pl.entries.size()));
+        CK(cudaMemcpy(d_entries_, pl.entries.data(), pl.entries.size(), cudaMemcpyHostToDevice));
+        ntiles_ = static_cast<uint32_t>(pl.tiles.size());
+        shapes_ = pl.shapes;
+        plan_has_box_ = pl.n_box > 0;
+        have_plan_ = true;
+        char buf[256];
+        snprintf(buf, sizeof buf, "tiles %dx%d of %dx%d px: %d box (TMA, %.2f B/px staged), %d gather, %d empty; entries %.2f B/px",
+                 pl.tiles_x, pl.tiles_y, kTileW, kTileH, pl.n_box, static_cast<double>(pl.box_bytes) / static_cast<double>(npix),
+                 pl.n_gather, pl.n_empty, static_cast<double>(pl.entries.size()) / static_cast<double>(npix));
+        plan_summary_ = buf;
+    }
     // frame slots depend on the sizes: rebuild lazily
     for (Slot *s : slots_) {
         cudaStreamDestroy(s->stream);
@@ -311,6 +580,143 @@ bool WarpDevice::warp(const void *d_faces, size_t face_stride, void *d_out, size
         err_ = "warp: at most 65535 frames per launch";
         return false;
     }
+    const size_t opx = rgba ? 4 : 1;
+    // the tiled kernel writes 4-pixel words at (y*W + x): needs W % 4 == 0 and aligned frames
+    const bool tiled_ok = have_plan_ && (width_ % 4 == 0) && (reinterpret_cast<uintptr_t>(d_out) % (4 * opx) == 0) &&
+                          (out_stride % (4 * opx) == 0 || nframes == 1) &&
+                          (!plan_has_box_ || (reinterpret_cast<uintptr_t>(d_faces) % 16 == 0 && (face_stride % 16 == 0 || nframes == 1)));
+    if (variant_ == BLINKY_KERNEL_GATHER || !tiled_ok) return launch_flat(d_faces, face_stride, d_out, out_stride, nframes, stream, rgba);
+    return launch_tiled(d_faces, face_stride, d_out, out_stride, nframes, stream, rgba);
+}
+
+WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stride, int nframes, void *stream) {
+    static uint64_t tick = 0;
+    ++tick;
+    for (TmapSet *t : tmap_sets_)
+        if (t->faces == d_faces && t->face_stride == face_stride && t->nframes == nframes) {
+            t->last_use = tick;
+            return t;
+        }
+    if (!encode_fn_) {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            fail("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)", e);
+            return nullptr;
+        }
+        encode_fn_ = fn;
+    }
+    TmapSet *t = nullptr;
+    if (tmap_sets_.size() >= 8) {  // recycle the least recently used table (its kernels are long gone)
+        t = tmap_sets_[0];
+        for (TmapSet *c : tmap_sets_)
+            if (c->last_use < t->last_use) t = c;
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    } else {
+        t = new TmapSet();
+        if (cudaMalloc(&t->d_table, sizeof(CUtensorMap) * 8 * kTmapRows) != cudaSuccess) {
+            delete t;
+            fail("cudaMalloc(tensor maps)", cudaGetLastError());
+            return nullptr;
+        }
+        tmap_sets_.push_back(t);
+    }
+    t->faces = d_faces;
+    t->face_stride = face_stride;
+    t->nframes = nframes;
+    t->last_use = tick;
+    std::vector<CUtensorMap> host(8 * kTmapRows);
+    memset(host.data(), 0, host.size() * sizeof(CUtensorMap));
+    const cuuint64_t ps = static_cast<cuuint64_t>(platesize_);
+    // 4-D view of the globe: (x, y, plate, frame)
+    const cuuint64_t dims[4] = {ps, ps, static_cast<cuuint64_t>(numplates_), static_cast<cuuint64_t>(nframes)};
+    const cuuint64_t fstride = nframes > 1 ? static_cast<cuuint64_t>(face_stride) : ps * ps * static_cast<cuuint64_t>(numplates_);
+    const cuuint64_t strides[3] = {ps, ps * ps, fstride};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (uint16_t shape : shapes_) {
+        const uint32_t w16 = shape >> 8, h8 = shape & 0xff;
+        const cuuint32_t box[4] = {w16 * 16, h8 * 8, 1, 1};
+        CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
+            &host[(w16 - 1) * kTmapRows + (h8 - 1)], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(d_faces), dims, strides,
+            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(box %ux%u, ps %d) failed with CUresult %d", w16 * 16, h8 * 8, platesize_, static_cast<int>(r));
+            err_ = buf;
+            t->faces = nullptr;
+            return nullptr;
+        }
+    }
+    if (cudaMemcpyAsync(t->d_table, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
+                        static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+        fail("cudaMemcpyAsync(tensor maps)", cudaGetLastError());
+        t->faces = nullptr;
+        return nullptr;
+    }
+    return t;
+}
+
+bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
+                              void *stream, bool rgba) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TiledParams p;
+    p.tiles = static_cast<const TileDesc *>(d_tiles_);
+    p.entries = d_entries_;
+    p.tmaps = nullptr;
+    if (plan_has_box_) {
+        TmapSet *t = get_tmaps(d_faces, face_stride, nframes, stream);
+        if (!t) return false;
+        p.tmaps = t->d_table;
+    }
+    p.faces = static_cast<const uint8_t *>(d_faces);
+    p.face_stride = face_stride;
+    p.bg = d_bg_;
+    p.lut = d_lut_;
+    p.rgba = d_rgba_;
+    p.out = d_out;
+    p.out_stride = out_stride;
+    p.ntiles = ntiles_;
+    p.nframes = static_cast<uint32_t>(nframes);
+    p.total = ntiles_ * static_cast<uint32_t>(nframes);
+    p.width = width_;
+    p.height = height_;
+    const bool rubix = rubix_;
+    const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
+    if (tiled_ctas_per_sm_[vi] == 0) {
+        int n = 0;
+        cudaError_t e;
+        const void *fn = rubix && rgba ? reinterpret_cast<const void *>(warp_tiled_kernel<true, true>)
+                         : rubix       ? reinterpret_cast<const void *>(warp_tiled_kernel<true, false>)
+                         : rgba        ? reinterpret_cast<const void *>(warp_tiled_kernel<false, true>)
+                                       : reinterpret_cast<const void *>(warp_tiled_kernel<false, false>);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTiledSmemBytes));
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(max dynamic smem)", e);
+        if (rubix && rgba) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<true, true>, kTiledThreads, kTiledSmemBytes);
+        else if (rubix) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<true, false>, kTiledThreads, kTiledSmemBytes);
+        else if (rgba) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<false, true>, kTiledThreads, kTiledSmemBytes);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<false, false>, kTiledThreads, kTiledSmemBytes);
+        if (e != cudaSuccess || n < 1) n = 4;
+        tiled_ctas_per_sm_[vi] = n;
+    }
+    uint32_t grid = static_cast<uint32_t>(sm_count_ * tiled_ctas_per_sm_[vi]);
+    if (grid > p.total) grid = p.total;
+    if (rubix && rgba) warp_tiled_kernel<true, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+    else if (rubix) warp_tiled_kernel<true, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+    else if (rgba) warp_tiled_kernel<false, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+    else warp_tiled_kernel<false, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+    char buf[200];
+    snprintf(buf, sizeof buf, "warp_tiled_kernel<rubix=%d,rgba=%d> grid=%u block=%d (%d CTAs/SM, persistent, %d-stage TMA ring)", rubix, rgba, grid,
+             kTiledThreads, tiled_ctas_per_sm_[vi], kStages);
+    last_kernel_ = buf;
+    ++launches_;
+    CK(cudaGetLastError());
+    return true;
+}
+
+bool WarpDevice::launch_flat(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+                             bool rgba) {
     // NULL is CUDA's default stream (what torch.cuda.current_stream() hands out
     // unless the caller made its own) — NOT this context's private stream.
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -13,7 +13,7 @@
 
 namespace blinky {
 
-struct TileInfo;  // defined in warp_device.cu
+struct TilePlan;  // tile_plan.h
 
 struct LensmapUpload {
     int width = 0, height = 0, platesize = 0, numplates = 0;
@@ -24,6 +24,7 @@ struct LensmapUpload {
     const int32_t *span_off = nullptr;       // [height+1]
     const int32_t *spans = nullptr;          // pairs
     size_t nspans = 0;
+    const TilePlan *plan = nullptr;          // tiled layout (may be null: flat kernels only)
 };
 
 class WarpDevice {
@@ -79,6 +80,27 @@ private:
     bool have_rgba_ = false;
     std::vector<int32_t> span_off_, spans_;
     int variant_ = 0;
+
+    // tiled layout (kernel K2)
+    struct TmapSet;
+    bool have_plan_ = false;
+    bool plan_has_box_ = false;
+    void *d_tiles_ = nullptr;       // TileDesc[]
+    uint8_t *d_entries_ = nullptr;
+    uint32_t ntiles_ = 0;
+    std::vector<uint16_t> shapes_;
+    std::vector<TmapSet *> tmap_sets_;   // small cache keyed by (faces ptr, stride, nframes)
+    void *encode_fn_ = nullptr;          // cuTensorMapEncodeTiled
+    int tiled_ctas_per_sm_[4] = {0, 0, 0, 0};
+    TmapSet *get_tmaps(const void *d_faces, size_t face_stride, int nframes, void *stream);
+    bool launch_tiled(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+                      bool rgba);
+    bool launch_flat(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+                     bool rgba);
+    std::string plan_summary_;
+public:
+    const std::string &plan_summary() const { return plan_summary_; }
+private:
 
     // e2e pipeline
     std::vector<Slot *> slots_;

@@ -198,6 +198,9 @@ int blinky_set_rgba_table(blinky_ctx *ctx, const uint32_t table[256]);
 int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_stride, void *d_out_rgba,
                             size_t out_stride, int nframes, void *stream);
 
+/* one-line description of how the current lensmap was tiled for the TMA kernel
+ * (tile counts per class, staged bytes per pixel); "" before a build */
+const char *blinky_plan_summary(blinky_ctx *ctx);
 /* number of kernel launches issued by this context so far */
 int64_t blinky_launch_count(blinky_ctx *ctx);
 /* last warp kernel's name and launch geometry, for reports */

@@ -67,7 +67,7 @@ def main():
                           ms=round(t * 1e3, 4), us_per_frame=round(t * 1e6 / nf, 2),
                           mpix_s=round(npix * nf / t / 1e6, 1), alg_gbs=round(alg / t / 1e9, 1),
                           frac_of_6485=round(alg / t / 1e9 / 6485.5, 3), kernel=fe.last_kernel,
-                          min_ms=round(min(times) * 1e3, 4))))
+                          min_ms=round(min(times) * 1e3, 4), plan=fe.plan_summary)))
 
 
 if __name__ == "__main__":

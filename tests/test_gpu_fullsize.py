@@ -1,0 +1,93 @@
+"""BASELINE's full-size configurations on the GPU (C2 1920x1080 / 6x1024^2, C3 3840x2160 /
+6x2048^2): exact parity against the oracle, which at these sizes still finishes in seconds
+because the lens is the C transcription, plus size-independent properties of the gather."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fe(bb, palette, cuda_device):
+    f = bb.Fisheye(device=cuda_device, palette=palette)
+    yield f
+    f.close()
+
+
+CONFIGS = [
+    ("C2", 1920, 1080, 1024, "cube", "panini", "f_fov 170", False),
+    ("C3", 3840, 2160, 2048, "cube", "quincuncial", "f_cover", True),
+    ("C4-panini", 3840, 2160, 2048, "cube", "panini", "f_fov 180", False),
+    ("C4-fisheye1", 3840, 2160, 2048, "cube", "fisheye1", "f_contain", False),
+    ("C5-trism", 3840, 2160, 2048, "trism", "stereographic", "f_fov 180", False),
+]
+
+
+@pytest.mark.parametrize("name,W,H,PS,globe,lens,zoom,rubix", CONFIGS)
+def test_full_size_parity_and_properties(bb, fe, restate, palette, name, W, H, PS, globe, lens, zoom, rubix):
+    import torch
+
+    threads = max(1, min(64, os.cpu_count() or 1))
+    fe.command(f"f_globe {globe}")
+    fe.command(f"f_lens {lens}")
+    fe.command(zoom)
+    fe.set_rubix(rubix)
+    fe.build_lensmap(W, H, PS, threads)
+    z = zoom.split()
+    om = restate.build(globe, lens, W, H, PS, zoom=(z[0], int(z[1]) if len(z) > 1 else 0))
+    idx, tint = fe.lensmap()
+    assert np.array_equal(idx, om["idx"]) and np.array_equal(tint, om["tint"])
+    assert fe.display() == om["display"] and fe.scale == om["scale"]
+    P = fe.numplates
+    bg = bb.synthetic_background(W, H)
+    fe.set_background(bg)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    d_faces = torch.randint(0, 256, (2, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+    faces = d_faces.cpu().numpy()
+    pm = restate.palmaps(palette)
+    want0 = restate.render(om["idx"], om["tint"], faces[0], pm, rubix, background=bg, threads=threads)
+    want1 = restate.render(om["idx"], om["tint"], faces[1], pm, rubix, background=bg, threads=threads)
+    for kernel in (0, 1):
+        fe.set_kernel(kernel)
+        d_out = torch.zeros((2, H, W), dtype=torch.uint8, device="cuda")
+        fe.warp(d_faces, d_out, nframes=2)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        assert np.array_equal(got[0], want0) and np.array_equal(got[1], want1), (name, kernel)
+    fe.set_kernel(0)
+
+    # property 1 — it is a pure gather: with torch's own index kernel as an independent
+    # implementation, out == where(valid, lut[tint][faces.flat[idx]], background)
+    t_idx = torch.from_numpy(idx.astype(np.int64)).cuda()
+    valid = t_idx >= 0
+    src = d_faces[0].reshape(-1)[t_idx.clamp(min=0)]
+    if rubix:
+        t_tint = torch.from_numpy(tint.astype(np.int64)).cuda()
+        lut = torch.from_numpy(np.concatenate([pm, np.arange(256, dtype=np.uint8)[None]]).astype(np.uint8)).cuda()
+        src = lut[t_tint.clamp(max=6).where(t_tint != 255, torch.full_like(t_tint, 6)), src.long()]
+    expect = torch.where(valid, src, torch.from_numpy(bg).cuda())
+    d_out = torch.zeros((2, H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(d_faces, d_out, nframes=2)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[0], expect)
+
+    # property 2 — constant faces give a constant image where mapped (through the LUT when on)
+    const = torch.full((1, P, PS, PS), 123, dtype=torch.uint8, device="cuda")
+    d_one = torch.zeros((1, H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(const, d_one, nframes=1)
+    torch.cuda.synchronize()
+    vals = torch.unique(d_one[0][valid])
+    allowed = {123} | ({int(pm[i][123]) for i in range(P)} if rubix else set())
+    assert set(vals.tolist()) <= allowed
+
+    # property 3 — idempotent and deterministic: same input twice, identical bytes
+    d_again = torch.zeros((2, H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(d_faces, d_again, nframes=2)
+    torch.cuda.synchronize()
+    assert torch.equal(d_again, d_out)
+
+    # property 4 — host path == device path at full size
+    host = fe.warp_host(faces.reshape(2, -1))
+    assert np.array_equal(host[0], want0) and np.array_equal(host[1], want1)
