@@ -354,9 +354,7 @@ class Fisheye:
         """pinned host memory as a numpy uint8 array (freed with free_pinned)"""
         p = c_void_p()
         self._check(self._lib.blinky_alloc_pinned(self._ctx, nbytes, ctypes.byref(p)))
-        arr = np.ctypeslib.as_array(ctypes.cast(p, POINTER(c_uint8)), shape=(nbytes,))
-        arr._blinky_ptr = p.value if hasattr(arr, "__dict__") else None
-        return arr
+        return np.ctypeslib.as_array(ctypes.cast(p, POINTER(c_uint8)), shape=(nbytes,))
 
     def free_pinned(self, arr: np.ndarray):
         self._check(self._lib.blinky_free_pinned(self._ctx, arr.ctypes.data))
