@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — the lens-warp benchmark (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+metric   lens-warp Mpixels/s (output pixels, W*H per frame) on the headline workload of
+         BASELINE.json: 3840x2160 screen, cube globe of 6x2048^2 8-bit faces, panini lens.
+step     one pass of the hot path over one batch of FRAMES distinct synthetic frames per GPU
+         (one kernel launch).  The frames of a batch are 16 x 25 MB = 403 MB of faces, larger
+         than the 126 MB L2, so every step streams its faces from HBM; the lensmap (static per
+         lens, like the reference's) is reused by all frames and stays L2-resident.
+value    whole-job throughput over all N GPUs with inputs resident in HBM (CUDA events on the
+         launch stream, max over ranks).  Frames are independent: rank r warps its own batch,
+         no collective on the data path ("weak" scaling); the NCCL gather of finished frames
+         to rank 0 that the reference topology needs is timed separately (key "gather").
+e2e      the same metric through the C ABI's host entry point blinky_warp_host: pinned host
+         faces -> cudaMemcpyAsync -> warp -> copy back, all inside the timed region.
+--impl reference   the reference's own CPU loop (oracle/_ref = unmodified fisheye.c compiled
+         headless; else the oracle port) on the host cores, same workload, bounded sample.
+
+The oracle (oracle/) is only ever the thing TIMED BESIDE or CHECKED AGAINST — never the
+product path, which raises if libblinky_b200.so is missing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, platesize, globe, lens, zoom command, rubix)
+    "4k-cube-panini": (3840, 2160, 2048, "cube", "panini", "f_fov 180", False),           # headline (metric)
+    "1080p-cube-panini170": (1920, 1080, 1024, "cube", "panini", "f_fov 170", False),     # BASELINE configs[1]
+    "4k-cube-quincuncial-rubix": (3840, 2160, 2048, "cube", "quincuncial", "f_cover", True),  # configs[2]
+    "4k-trism-stereographic": (3840, 2160, 2048, "trism", "stereographic", "f_fov 180", False),  # configs[4]
+    "4k-cube-stereographic": (3840, 2160, 2048, "cube", "stereographic", "f_fov 180", False),
+    "4k-cube-equirect": (3840, 2160, 2048, "cube", "equirect", "f_contain", False),
+    "4k-cube-hammer": (3840, 2160, 2048, "cube", "hammer", "f_contain", False),
+    "4k-cube-fisheye1": (3840, 2160, 2048, "cube", "fisheye1", "f_contain", False),
+    "c1-640x480": (640, 480, 256, "cube", "panini", "f_fov 180", False),                  # configs[0]
+}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons, sampled with NVML while the load runs"""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+
+    def summary(self, note: str):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "note": note}
+
+
+def cpu_baseline(workload, threads_all: bool = False):
+    """The reference's CPU loop on this box: oracle/_ref (kind 'reference') when it was built,
+    else the plain-C port (kind 'port').  Bounded sample: a few seconds of render_lensmap."""
+    import blinky_b200 as bb
+    from oracle.pyoracle import RefOracle, Restatement
+
+    W, H, PS, globe, lens, zoom, rubix = workload
+    pal = bb.synthetic_palette()
+    faces = bb.synthetic_faces(6 if globe != "trism" else 5, PS, 0)
+    out = {}
+    if RefOracle.available():
+        R = RefOracle.get(bb.SCRIPT_DIR, pal)
+        R.set_screen(W, H)
+        R.command(f"f_globe {globe}")
+        R.command(f"f_lens {lens}")
+        R.command(zoom)
+        if R.rubix_enabled != rubix:
+            R.command("f_rubix")
+        t0 = time.time()
+        R.build(W, H, PS)
+        build_s = time.time() - t0
+        R.render(faces, None)  # loads the faces into globe.pixels
+        best1, _ = R.time_render(1)
+        reps = int(max(3, min(200, 4.0 / max(best1, 1e-4))))
+        best, total = R.time_render(reps)
+        out = {"value": round(W * H / best / 1e6, 1), "unit": "Mpixels/s", "cores": 1, "kind": "reference",
+               "sample": f"{reps} x render_lensmap() of one {W}x{H} frame, unmodified fisheye.c compiled -O2 (oracle/_ref), "
+                         f"single thread as in the engine; best call; lensmap build {build_s:.1f} s not counted",
+               "mean_value": round(W * H * reps / total / 1e6, 1)}
+        idx, tint = R.lensmap()
+    else:
+        with bb.Fisheye(device=None, palette=pal) as fe:
+            fe.command(f"f_globe {globe}")
+            fe.command(f"f_lens {lens}")
+            fe.command(zoom)
+            fe.build_lensmap(W, H, PS, os.cpu_count() or 1)
+            idx, tint = fe.lensmap()
+    O = Restatement()
+    pm = O.palmaps(pal)
+    if not out:
+        best1, _ = O.time_render(idx, tint, faces, pm, rubix, 1, 1)
+        reps = int(max(3, min(200, 4.0 / max(best1, 1e-4))))
+        best, total = O.time_render(idx, tint, faces, pm, rubix, 1, reps)
+        out = {"value": round(W * H / best / 1e6, 1), "unit": "Mpixels/s", "cores": 1, "kind": "port",
+               "sample": f"{reps} x restated render_lensmap (oracle/blinky_oracle.c) of one {W}x{H} frame, single thread; best call",
+               "mean_value": round(W * H * reps / total / 1e6, 1)}
+    nthreads = O.max_threads()
+    bestn, _ = O.time_render(idx, tint, faces, pm, rubix, nthreads, 20)
+    out["all_cores_port"] = {"value": round(W * H / bestn / 1e6, 1), "unit": "Mpixels/s", "cores": nthreads,
+                             "note": "same loop, rows split over all host threads (oracle port; the reference itself is single-threaded)"}
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation, same metric/config/unit."""
+    if rank != 0:
+        return
+    workload = WORKLOADS[args.workload]
+    W, H, PS, globe, lens, zoom, rubix = workload
+    import blinky_b200 as bb
+    from oracle.pyoracle import RefOracle, Restatement
+
+    pal = bb.synthetic_palette()
+    P = 5 if globe == "trism" else 6
+    frames_per_step = 4
+    faces = [bb.synthetic_faces(P, PS, f) for f in range(frames_per_step)]
+    if RefOracle.available():
+        R = RefOracle.get(bb.SCRIPT_DIR, pal)
+        R.set_screen(W, H)
+        for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
+            R.command(c)
+        if R.rubix_enabled != rubix:
+            R.command("f_rubix")
+        R.build(W, H, PS)
+        kind, cores = "reference", 1
+
+        def step():
+            for f in faces:
+                R.render(f, None)  # memcpy of the plates into globe.pixels (render_plate's job) + render_lensmap
+    else:
+        with bb.Fisheye(device=None, palette=pal) as fe:
+            for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
+                fe.command(c)
+            fe.build_lensmap(W, H, PS, os.cpu_count() or 1)
+            idx, tint = fe.lensmap()
+        O = Restatement()
+        pm = O.palmaps(pal)
+        kind, cores = "port", 1
+
+        def step():
+            for f in faces:
+                O.render(idx, tint, f, pm, rubix)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = W * H * frames_per_step * args.steps / dt / 1e6
+    line = {"impl": "reference", "metric": "lens-warp Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "screen": [W, H], "globe": globe, "platesize": PS, "lens": lens, "zoom": zoom,
+                       "rubix": rubix, "frames_per_step": frames_per_step},
+            "cpu_baseline": {"value": round(value, 1), "unit": "Mpixels/s", "cores": cores, "kind": kind,
+                             "sample": f"{frames_per_step} frames per step: plate copy into globe.pixels + render_lensmap, "
+                                       f"single thread (the reference's loop has no threading)"},
+            "e2e": {"value": round(value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="4k-cube-panini", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=16, help="distinct frames per GPU per step")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (tiled TMA), 1 flat gather")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import blinky_b200 as bb  # raises if the CUDA extension is missing — there is no fallback
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from blinky_b200.sharding import frames_for_rank, gather_frames
+
+    W, H, PS, globe, lens, zoom, rubix = WORKLOADS[args.workload]
+    F = args.frames
+    fe = bb.Fisheye(device=local_rank, palette=bb.synthetic_palette())
+    for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
+        fe.command(c)
+    fe.set_rubix(rubix)
+    t0 = time.time()
+    threads = max(1, min(64, (os.cpu_count() or 1) // max(1, world)))
+    fe.build_lensmap(W, H, PS, threads)  # every rank rebuilds deterministically: nothing to broadcast
+    build_s = time.time() - t0
+    fe.set_kernel(args.kernel)
+    P, M, npix = fe.numplates, fe.mapped_pixels, W * H
+    my_frames = frames_for_rank(F * world, rank, world)  # global frame ids of this rank's batch
+    gen = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    d_faces = torch.randint(0, 256, (F, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+    d_out = torch.zeros((F, H, W), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        fe.warp(d_faces, d_out, nframes=F, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = fe.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = fe.launch_count - launches0
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    # the timed region is a few milliseconds: keep the identical load running so that NVML
+    # (which refreshes every few ms) actually sees the clocks this kernel runs at
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    sampler.stop()
+    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    value = world * F * args.steps * npix / elapsed / 1e6
+
+    # ---- end to end through the C ABI's host entry point ---------------------------------
+    h_faces = fe.alloc_pinned(F * P * PS * PS)
+    h_out = fe.alloc_pinned(F * npix)
+    h_faces[:] = d_faces.cpu().numpy().reshape(-1)
+    e2e_steps = max(2, min(args.steps, 6))
+    fe.warp_host(h_faces, h_out.reshape(F, H, W))  # warm-up (allocates the frame ring)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fe.warp_host(h_faces, h_out.reshape(F, H, W))
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    same = bool(np.array_equal(h_out.reshape(F, H, W)[F - 1], d_out[F - 1].cpu().numpy()))
+    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * F * e2e_steps * npix / float(te.item()) / 1e6
+    shown = sum(fe.display())
+    fe.free_pinned(h_faces)
+    fe.free_pinned(h_out)
+
+    # ---- the final gather to rank 0 (reference topology), timed on its own ---------------
+    gather = None
+    if world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gathered = gather_frames(d_out, rank, world)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) * 1e-3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gsec = float(tg.item())
+        gather = {"ms": round(gsec * 1e3, 3), "bytes_into_rank0": (world - 1) * F * npix,
+                  "GBs_into_rank0": round((world - 1) * F * npix / gsec / 1e9, 1), "included_in_value": False,
+                  "value_with_gather": round(world * F * npix / (elapsed / args.steps + gsec) / 1e6, 1),
+                  "how": "torch.distributed (NCCL) send/recv of each rank's finished uint8 frames to rank 0"}
+        if rank == 0:
+            assert gathered.shape[0] == world * F
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = (5 * npix + M) * F  # 4 B lensmap entry + 1 B source (mapped) + 1 B output per pixel
+        launch_s = elapsed / max(1, launches)
+        achieved = alg_bytes / launch_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:  # noqa: BLE001
+            pass
+        line = {
+            "metric": "lens-warp Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(elapsed / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "screen": [W, H], "globe": globe, "numplates": P, "platesize": PS, "lens": lens,
+                       "zoom": zoom, "rubix": rubix, "frames_per_gpu_per_step": F, "global_batch_frames": F * world,
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "l2": "inputs larger than L2 (403 MB of distinct faces per step); lensmap reused across frames by design",
+                       "mapped_pixel_fraction": round(M / npix, 4), "lensmap_build_s": round(build_s, 2), "tiling": fe.plan_summary},
+            "kernel": fe.last_kernel, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "launch_us": round(launch_s * 1e6, 2),
+                         "note": "achieved = (5*W*H + M) bytes/frame x frames per launch / CUDA-event time of the launch"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": int(shown * PS * PS * F),
+                    "d2h_bytes_per_step": int(npix * F), "steps": e2e_steps, "matches_device_path": same,
+                    "how": "blinky_warp_host: pinned host faces -> cudaMemcpyAsync (only plates the lens shows) -> kernel -> "
+                           "cudaMemcpy2DAsync back, 3-slot stream pipeline; wall clock around synchronous calls"},
+            "clocks": sampler.summary("sampled by NVML over the timed region plus 1 s of the identical load"),
+        }
+        if gather:
+            line["gather"] = gather
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(WORKLOADS[args.workload])
+        print(json.dumps(line))
+    fe.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

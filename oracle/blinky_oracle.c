@@ -576,3 +576,24 @@ int orc_max_threads(void)
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+/* Wall-clock timing of the restated hot loop for the CPU baseline: `reps` calls,
+ * returns the best single call in seconds, *total_seconds the sum. */
+#include <time.h>
+double orc_time_render(const orc_lensmap *lm, const uint8_t *faces, const uint8_t palmaps[ORC_MAX_PLATES][256],
+                       int rubix_enabled, uint8_t *vbuf, int rowbytes, int threads, int reps, double *total_seconds)
+{
+    double best = 1e30, total = 0;
+    for (int r = 0; r < reps; r++) {
+        struct timespec a, b;
+        clock_gettime(CLOCK_MONOTONIC, &a);
+        if (threads > 1) orc_render_lensmap_omp(lm, faces, palmaps, rubix_enabled, vbuf, rowbytes, 0, 0, threads);
+        else orc_render_lensmap(lm, faces, palmaps, rubix_enabled, vbuf, rowbytes, 0, 0);
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        double dt = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+        if (dt < best) best = dt;
+        total += dt;
+    }
+    if (total_seconds) *total_seconds = total;
+    return best;
+}

@@ -105,6 +105,8 @@ void orc_render_lensmap(const orc_lensmap *lm, const uint8_t *faces, const uint8
 void orc_render_lensmap_omp(const orc_lensmap *lm, const uint8_t *faces, const uint8_t palmaps[ORC_MAX_PLATES][256],
                             int rubix_enabled, uint8_t *vbuf, int rowbytes, int vrect_x, int vrect_y, int threads);
 int orc_max_threads(void);
+double orc_time_render(const orc_lensmap *lm, const uint8_t *faces, const uint8_t palmaps[ORC_MAX_PLATES][256],
+                       int rubix_enabled, uint8_t *vbuf, int rowbytes, int threads, int reps, double *total_seconds);
 
 /* --- C transcriptions of shipped scripts (oracle_lenses.c) -------------- */
 /* name: "panini","stereographic","equirect","hammer","fisheye1","fisheye2",

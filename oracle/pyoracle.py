@@ -197,6 +197,22 @@ class Restatement:
         L.orc_render_lensmap.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int]
         L.orc_render_lensmap_omp.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]
 
+    def time_render(self, idx, tint, faces, palmaps, rubix: bool, threads: int, reps: int):
+        """(best seconds, total seconds) of `reps` calls of the restated render_lensmap"""
+        h, w = idx.shape
+        idx = np.ascontiguousarray(idx, np.int32)
+        tint = np.ascontiguousarray(tint, np.uint8)
+        faces = np.ascontiguousarray(faces, np.uint8)
+        palmaps = np.ascontiguousarray(palmaps, np.uint8)
+        out = np.zeros((h, w), np.uint8)
+        LM = _LensMap(w, h, 0.0, idx.ctypes.data, tint.ctypes.data)
+        total = c_double()
+        self.lib.orc_time_render.restype = c_double
+        self.lib.orc_time_render.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, POINTER(c_double)]
+        best = self.lib.orc_time_render(ctypes.byref(LM), _p(faces), _p(palmaps), int(rubix), _p(out), w, threads, reps,
+                                        ctypes.byref(total))
+        return best, total.value
+
     def max_threads(self) -> int:
         return self.lib.orc_max_threads()
 
