@@ -313,8 +313,8 @@ const char *blinky_plan_summary(blinky_ctx *ctx) {
                                                  ctx->host.platesize(), ctx->host.platesize() % 16 == 0);
     const double npix = static_cast<double>(ctx->host.width()) * ctx->host.height();
     char buf[256];
-    snprintf(buf, sizeof buf, "tiles %dx%d of %dx%d px: %d box (TMA, %.3f B/px staged, %zu shapes), %d gather, %d empty; entries %.3f B/px",
-             pl.tiles_x, pl.tiles_y, blinky::kTileW, blinky::kTileH, pl.n_box, static_cast<double>(pl.box_bytes) / npix,
+    snprintf(buf, sizeof buf, "tiles %dx%d of %dx%d px: %d box (%d fully mapped; TMA, %.3f B/px staged, %zu shapes), %d gather, %d empty; entries %.3f B/px",
+             pl.tiles_x, pl.tiles_y, blinky::kTileW, blinky::kTileH, pl.n_box, pl.n_box_full, static_cast<double>(pl.box_bytes) / npix,
              pl.shapes.size(), pl.n_gather, pl.n_empty, static_cast<double>(pl.entries.size()) / npix);
     ctx->scratch = buf;
     return ctx->scratch.c_str();

@@ -24,6 +24,7 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
             const int x0 = tx * kTileW, y0 = ty * kTileH;
             // collect the tile (pixels beyond the frame edge are unmapped)
             bool any = false, one_plate = true;
+            int nvalid = 0;
             uint32_t plate = 0;
             uint32_t minx = ~0u, miny = ~0u, maxx = 0, maxy = 0;
             for (int r = 0; r < kTileH; ++r) {
@@ -32,6 +33,7 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
                     if (y0 + r < height && x0 + c < width) e = packed[static_cast<size_t>(y0 + r) * width + x0 + c];
                     tile[static_cast<size_t>(r) * kTileW + c] = e;
                     if (!(e & BLINKY_LM_VALID)) continue;
+                    ++nvalid;
                     const uint32_t idx = e & BLINKY_LM_INDEX_MASK;
                     const uint32_t p = idx / ps2, rem = idx % ps2;
                     const uint32_t py = rem / ps, px = rem % ps;
@@ -72,7 +74,8 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
             plan.entries.resize((plan.entries.size() + 15) / 16 * 16);
             d.entry_offset = static_cast<uint32_t>(plan.entries.size());
             if (box) {
-                d.type = TILE_BOX;
+                d.type = nvalid == kTilePixels ? TILE_BOX_FULL : TILE_BOX;
+                if (nvalid == kTilePixels) ++plan.n_box_full;
                 d.plate = static_cast<uint8_t>(plate);
                 d.box_x = static_cast<int16_t>(minx);
                 d.box_y = static_cast<int16_t>(miny);
@@ -106,6 +109,9 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
         }
     }
     plan.entries.resize((plan.entries.size() + 15) / 16 * 16 + 16);
+    // BOX tiles first: the TMA ring kernel walks [0, n_box), the gather kernel the rest
+    std::stable_partition(plan.tiles.begin(), plan.tiles.end(),
+                          [](const TileDesc &d) { return d.type == TILE_BOX || d.type == TILE_BOX_FULL; });
     return plan;
 }
 

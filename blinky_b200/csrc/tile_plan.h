@@ -28,7 +28,9 @@ constexpr int kTileH = 32;
 constexpr int kTilePixels = kTileW * kTileH;
 constexpr int kMaxBoxBytes = 4096;
 
-enum TileType : uint8_t { TILE_EMPTY = 0, TILE_BOX = 1, TILE_GATHER = 2 };
+// TILE_BOX_FULL: a BOX tile whose 1024 pixels are all mapped and inside the frame
+// (the kernel skips every per-pixel validity / background test for it)
+enum TileType : uint8_t { TILE_EMPTY = 0, TILE_BOX = 1, TILE_GATHER = 2, TILE_BOX_FULL = 3 };
 
 // 16-bit entry of a BOX tile
 constexpr uint16_t kBoxValid = 0x8000;
@@ -49,10 +51,10 @@ static_assert(sizeof(TileDesc) == 16, "TileDesc layout is part of the kernel ABI
 struct TilePlan {
     int width = 0, height = 0, platesize = 0;
     int tiles_x = 0, tiles_y = 0;
-    std::vector<TileDesc> tiles;
+    std::vector<TileDesc> tiles;        // BOX / BOX_FULL tiles first (n_box of them), then GATHER and EMPTY tiles
     std::vector<uint8_t> entries;       // all entry blocks, tile-ordered
     std::vector<uint16_t> shapes;       // distinct (w16 << 8 | h8) used by BOX tiles
-    int n_empty = 0, n_box = 0, n_gather = 0;
+    int n_empty = 0, n_box = 0, n_gather = 0, n_box_full = 0;  // n_box includes n_box_full
     uint64_t box_bytes = 0;             // sum of staged box sizes (bytes per frame through TMA)
 };
 

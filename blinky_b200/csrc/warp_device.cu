@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // globe directly, with the same 2-D thread layout (a warp covers 32x4 pixels).
 // --------------------------------------------------------------------------
 constexpr int kStages = 4;
-constexpr int kConsumerWarps = kThreads / 32;          // 8
-constexpr int kTiledThreads = kThreads + 32;           // + producer warp
+constexpr int kConsumerWarps = 4;
+constexpr int kConsumerThreads = kConsumerWarps * 32;   // 128: each owns two 4-pixel quads of a 32x32 tile
+constexpr int kTiledThreads = kConsumerThreads + 32;    // + producer warp
 constexpr int kTmapRows = 32;  // descriptor table index = (w16-1)*kTmapRows + (h8-1)
 
 struct TiledParams {
@@ -203,8 +204,8 @@ struct TiledParams {
 };
 
 struct __align__(128) TiledStage {
-    uint8_t box[kMaxBoxBytes];          // TMA destination (128-byte aligned)
-    uint8_t entries[kTilePixels * 4];   // 2 KB used by BOX tiles, 4 KB by GATHER tiles
+    uint8_t box[kMaxBoxBytes];          // TMA destination; GATHER tiles put their 4 KB of 32-bit entries here instead
+    uint8_t entries[kTilePixels * 2];   // 16-bit entries of BOX tiles
     uint4 desc;                         // TileDesc
     uint32_t frame;
     uint32_t pad[3];
@@ -220,6 +221,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Releases a pipeline stage AFTER the values read from it have really arrived in
+// registers.  A shared-memory load is only complete when its destination register is
+// written; `mbarrier.arrive` does not wait for in-flight LDS (seen in SASS: the arrive
+// issued right behind eight pending LDS, and the producer's next TMA then raced them).
+// Passing a value computed from every loaded register as an (unused) asm input makes
+// the scoreboard hold the arrive until those loads have landed.
+__device__ __forceinline__ void mbar_release_after(uint64_t *bar, uint32_t loaded_values) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(smem_u32(bar)), "r"(loaded_values) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -249,8 +259,92 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, 
                  : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// one quad (4 consecutive pixels) of a BOX tile: e2 holds its four 16-bit entries
+template <bool RUBIX, bool FULL>
+__device__ __forceinline__ void box_quad(const uint8_t *__restrict__ box, const uint8_t *__restrict__ s_lut, uint2 e2,
+                                         uint32_t (&px)[4], uint32_t &valid) {
+    const uint32_t ent[4] = {e2.x & 0xffffu, e2.x >> 16, e2.y & 0xffffu, e2.y >> 16};
+    valid = 0xfu;
+    if (!FULL) valid = ((ent[0] >> 15) & 1u) | ((ent[1] >> 14) & 2u) | ((ent[2] >> 13) & 4u) | ((ent[3] >> 12) & 8u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // unmapped entries carry offset 0: the read is harmless and its value is replaced below
+        uint32_t b = box[ent[k] & kBoxOffsetMask];
+        if (RUBIX) {
+            const uint32_t t = (ent[k] >> kBoxTintShift) & 7u;
+            if (t != BLINKY_LM_TINT_NONE) b = s_lut[t * 256 + b];
+        }
+        px[k] = b;
+    }
+}
+
+// GATHER tile (plate seams, singular points, strong minification): 32-bit entries,
+// direct global reads.  Layout differs from the BOX path on purpose: a warp takes
+// 8 tile rows and lane l is column l, so one warp-level load covers 32 consecutive
+// screen pixels of ONE row — neighbouring texels of at most a few plate rows —
+// instead of an 8x4 patch that touches 4x as many 32-byte sectors.
 template <bool RUBIX, bool RGBA>
-__global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledParams p) {
+__device__ __forceinline__ void gather_tile(const TiledParams &p, const uint32_t *__restrict__ ent32, const uint8_t *__restrict__ faces,
+                                            const uint8_t *__restrict__ s_lut, const uint32_t *__restrict__ s_rgba, uint8_t *out_frame,
+                                            uint32_t tile_x, uint32_t tile_y, uint32_t warp, uint32_t lane, uint64_t *empty_bar) {
+    uint32_t e[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = ent32[(warp * 8 + j) * kTileW + lane];
+    __syncwarp();
+    // entries are in registers: the stage can be refilled
+    if (lane == 0) mbar_release_after(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = 0;
+        if (e[j] & BLINKY_LM_VALID) v[j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
+    }
+    const uint32_t x = tile_x + lane;
+    if (x >= static_cast<uint32_t>(p.width)) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t y = tile_y + warp * 8 + j;
+        if (y < static_cast<uint32_t>(p.height)) {
+            const uint32_t pix = y * static_cast<uint32_t>(p.width) + x;
+            uint32_t b = v[j];
+            if (e[j] & BLINKY_LM_VALID) {
+                if (RUBIX) {
+                    const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                    if (t != BLINKY_LM_TINT_NONE) b = s_lut[t * 256 + b];
+                }
+            } else {
+                b = __ldg(p.bg + pix);
+            }
+            if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[b];
+            else out_frame[pix] = static_cast<uint8_t>(b);
+        }
+    }
+}
+
+template <bool RGBA>
+__device__ __forceinline__ void store_quad(void *out_frame, const uint32_t *__restrict__ s_rgba, uint32_t quad_index,
+                                           const uint32_t (&px)[4]) {
+    if (RGBA) {
+        st_stream_v4(static_cast<uint4 *>(out_frame) + quad_index, make_uint4(s_rgba[px[0]], s_rgba[px[1]], s_rgba[px[2]], s_rgba[px[3]]));
+    } else {
+        st_stream_u32(static_cast<uint32_t *>(out_frame) + quad_index, pack4(px[0], px[1], px[2], px[3]));
+    }
+}
+
+__device__ __forceinline__ void patch_background(const uint8_t *__restrict__ bg, uint32_t pix, uint32_t valid, uint32_t (&px)[4]) {
+    if (valid != 0xfu) {
+        const uint32_t bgw = __ldg(reinterpret_cast<const uint32_t *>(bg + pix));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (!((valid >> k) & 1u)) px[k] = (bgw >> (8 * k)) & 0xffu;
+    }
+}
+
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TiledStage *stages = reinterpret_cast<TiledStage *>(smem_raw);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(TiledStage) * kStages);
@@ -278,9 +372,9 @@ __global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledPa
     __syncthreads();
 
     const uint32_t G = gridDim.x;
-    if (tid >= kThreads) {
+    if (tid >= kConsumerThreads) {
         // ------------------------------ producer warp ------------------------------
-        if (tid == kThreads) {
+        if (tid == kConsumerThreads) {
             uint32_t w = blockIdx.x;
             uint4 next = make_uint4(0, 0, 0, 0);
             if (w < p.total) next = __ldg(reinterpret_cast<const uint4 *>(p.tiles + w / p.nframes));
@@ -295,7 +389,7 @@ __global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledPa
                 st.desc = d;
                 st.frame = frame;
                 const uint32_t type = (d.z >> 8) & 0xffu;
-                if (type == TILE_BOX) {
+                if (type == TILE_BOX || type == TILE_BOX_FULL) {
                     const uint32_t w16 = (d.z >> 16) & 0xffu, h8 = d.z >> 24;
                     const uint32_t box_bytes = w16 * 16u * h8 * 8u;
                     mbar_expect_tx(&full_bar[stage], box_bytes + kTilePixels * 2);
@@ -305,7 +399,7 @@ __global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledPa
                     bulk_copy_g2s(st.entries, p.entries + d.x, kTilePixels * 2, &full_bar[stage]);
                 } else if (type == TILE_GATHER) {
                     mbar_expect_tx(&full_bar[stage], kTilePixels * 4);
-                    bulk_copy_g2s(st.entries, p.entries + d.x, kTilePixels * 4, &full_bar[stage]);
+                    bulk_copy_g2s(st.box, p.entries + d.x, kTilePixels * 4, &full_bar[stage]);
                 } else {
                     mbar_arrive(&full_bar[stage]);
                 }
@@ -315,7 +409,9 @@ __global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledPa
     }
 
     // -------------------------------- consumers --------------------------------
-    const uint32_t row = tid >> 3, qx = tid & 7, lane = tid & 31;
+    // thread t owns quad (row t/8, column t%8) and the quad 16 rows below it
+    const uint32_t qx4 = (tid & 7u) * 4u, row = tid >> 3, lane = tid & 31u;
+    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
     uint32_t it = 0;
     for (uint32_t w = blockIdx.x; w < p.total; w += G, ++it) {
         const uint32_t stage = it % kStages, round = it / kStages;
@@ -324,59 +420,122 @@ __global__ void __launch_bounds__(kTiledThreads) warp_tiled_kernel(const TiledPa
         const uint4 d = st.desc;
         const uint32_t frame = st.frame;
         const uint32_t type = (d.z >> 8) & 0xffu;
-        const uint32_t x = (d.w & 0xffffu) + qx * 4, y = (d.w >> 16) + row;
-        const bool inside = x < static_cast<uint32_t>(p.width) && y < static_cast<uint32_t>(p.height);
+        const uint32_t x = (d.w & 0xffffu) + qx4, y0 = (d.w >> 16) + row;
+        const uint32_t pix0 = y0 * width + x, pix1 = pix0 + 16u * width;
+        uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
 
-        uint32_t v[4] = {0, 0, 0, 0};
-        uint32_t tint[4] = {7, 7, 7, 7};
-        uint32_t valid = 0;  // bit k: pixel k is mapped
+        uint32_t pa[4], pb[4], va = 0, vb = 0;
+        if (type == TILE_BOX_FULL) {
+            const uint2 ea = reinterpret_cast<const uint2 *>(st.entries)[tid];
+            const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
+            box_quad<RUBIX, true>(st.box, s_lut, ea, pa, va);
+            box_quad<RUBIX, true>(st.box, s_lut, eb, pb, vb);
+            __syncwarp();
+            if (lane == 0) mbar_release_after(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3]);
+            store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
+            store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
+            continue;
+        }
         if (type == TILE_BOX) {
-            const uint2 e2 = reinterpret_cast<const uint2 *>(st.entries)[tid];
-            const uint32_t ent[4] = {e2.x & 0xffffu, e2.x >> 16, e2.y & 0xffffu, e2.y >> 16};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (ent[k] & kBoxValid) {
-                    valid |= 1u << k;
-                    v[k] = st.box[ent[k] & kBoxOffsetMask];
-                    tint[k] = (ent[k] >> kBoxTintShift) & 7u;
-                }
-            }
+            const uint2 ea = reinterpret_cast<const uint2 *>(st.entries)[tid];
+            const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
+            box_quad<RUBIX, false>(st.box, s_lut, ea, pa, va);
+            box_quad<RUBIX, false>(st.box, s_lut, eb, pb, vb);
         } else if (type == TILE_GATHER) {
-            const uint4 e4 = reinterpret_cast<const uint4 *>(st.entries)[tid];
-            const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(frame) * p.face_stride;
-            const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+            gather_tile<RUBIX, RGBA>(p, reinterpret_cast<const uint32_t *>(st.box), p.faces + static_cast<size_t>(frame) * p.face_stride,
+                                     s_lut, s_rgba, out_frame, d.w & 0xffffu, d.w >> 16, tid >> 5, lane, &empty_bar[stage]);
+            continue;
+        } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (ent[k] & BLINKY_LM_VALID) {
-                    valid |= 1u << k;
-                    v[k] = ld_face(faces + (ent[k] & BLINKY_LM_INDEX_MASK));
-                    tint[k] = (ent[k] >> BLINKY_LM_TINT_SHIFT) & 7u;
-                }
+            for (int k = 0; k < 4; ++k) pa[k] = pb[k] = 0;
+        }
+        // everything this warp needs from the stage is in registers: hand the stage back
+        __syncwarp();
+        if (lane == 0)
+            mbar_release_after(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame);
+        if (x < width) {
+            if (y0 < height) {
+                patch_background(p.bg, pix0, va, pa);
+                store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
+            }
+            if (y0 + 16u < height) {
+                patch_background(p.bg, pix1, vb, pb);
+                store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
             }
         }
-        // the stage's shared memory has been consumed into registers: hand it back
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+}
 
-        if (inside) {
-            const size_t pix = static_cast<size_t>(y) * p.width + x;
-            uint32_t bgw = 0;
-            if (valid != 0xfu) bgw = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
-            uint32_t px[4];
+
+// --------------------------------------------------------------------------
+// K3: companion of K2 for the tiles TMA staging cannot serve (GATHER: plate seams,
+// singular points, strong minification; EMPTY: background only).  These are bound
+// by global-memory latency, so instead of the ring they get plain parallelism:
+// grid = (tiles, frame groups), 256 threads, a warp owns 4 tile rows and lane l is
+// column l (one warp-level load = 32 consecutive screen pixels of one row).  The
+// tile's entries are fetched once and reused for every frame of the group.
+// --------------------------------------------------------------------------
+constexpr int kGatherFramesPerCta = 4;
+
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kThreads) warp_tile_gather_kernel(const TiledParams p, const uint32_t first_tile) {
+    const uint32_t tid = threadIdx.x;
+    const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + first_tile + blockIdx.x));
+    const uint32_t type = (d.z >> 8) & 0xffu;
+    const uint32_t tile_x = d.w & 0xffffu, tile_y = d.w >> 16;
+    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
+    const uint32_t f0 = blockIdx.y * kGatherFramesPerCta;
+    const uint32_t f1 = min(f0 + kGatherFramesPerCta, p.nframes);
+
+    if (type == TILE_EMPTY) {
+        // quad layout: thread t copies 4 background pixels of row t/8
+        const uint32_t x = tile_x + (tid & 7u) * 4u, y = tile_y + (tid >> 3);
+        if (x >= width || y >= height) return;
+        const uint32_t pix = y * width + x;
+        const uint32_t bgw = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
+        const uint32_t px[4] = {bgw & 0xffu, (bgw >> 8) & 0xffu, (bgw >> 16) & 0xffu, bgw >> 24};
+        for (uint32_t f = f0; f < f1; ++f) {
+            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
+            if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(o) + (pix >> 2), make_uint4(__ldg(p.rgba + px[0]), __ldg(p.rgba + px[1]), __ldg(p.rgba + px[2]), __ldg(p.rgba + px[3])));
+            else st_stream_u32(reinterpret_cast<uint32_t *>(o) + (pix >> 2), bgw);
+        }
+        return;
+    }
+
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t x = tile_x + lane;
+    const uint32_t *__restrict__ ent32 = reinterpret_cast<const uint32_t *>(p.entries + d.x);
+    uint32_t e[4], bgv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t b = v[k];
-                if (RUBIX) {
-                    if (tint[k] != BLINKY_LM_TINT_NONE) b = s_lut[tint[k] * 256 + b];
+    for (int j = 0; j < 4; ++j) e[j] = __ldg(ent32 + (warp * 4 + j) * kTileW + lane);
+    if (x >= width) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t y = tile_y + warp * 4 + j;
+        bgv[j] = 0;
+        if (!(e[j] & BLINKY_LM_VALID) && y < height) bgv[j] = __ldg(p.bg + y * width + x);
+    }
+    for (uint32_t f = f0; f < f1; ++f) {
+        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f) * p.face_stride;
+        uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = bgv[j];
+            if (e[j] & BLINKY_LM_VALID) v[j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t y = tile_y + warp * 4 + j;
+            if (y < height) {
+                uint32_t b = v[j];
+                if (RUBIX && (e[j] & BLINKY_LM_VALID)) {
+                    const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                    if (t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
                 }
-                if (!((valid >> k) & 1u)) b = (bgw >> (8 * k)) & 0xffu;
-                px[k] = b;
-            }
-            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
-            if (RGBA) {
-                st_stream_v4(reinterpret_cast<uint4 *>(o) + (pix >> 2), make_uint4(s_rgba[px[0]], s_rgba[px[1]], s_rgba[px[2]], s_rgba[px[3]]));
-            } else {
-                st_stream_u32(reinterpret_cast<uint32_t *>(o) + (pix >> 2), px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24));
+                const uint32_t pix = y * width + x;
+                if (RGBA) reinterpret_cast<uint32_t *>(o)[pix] = __ldg(p.rgba + b);
+                else o[pix] = static_cast<uint8_t>(b);
             }
         }
     }
@@ -527,6 +686,7 @@ bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
         CK(cudaMalloc(&d_entries_, pl.entries.size()));
         CK(cudaMemcpy(d_entries_, pl.entries.data(), pl.entries.size(), cudaMemcpyHostToDevice));
         ntiles_ = static_cast<uint32_t>(pl.tiles.size());
+        nbox_tiles_ = static_cast<uint32_t>(pl.n_box);
         shapes_ = pl.shapes;
         plan_has_box_ = pl.n_box > 0;
         have_plan_ = true;
@@ -677,9 +837,15 @@ bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_o
     p.rgba = d_rgba_;
     p.out = d_out;
     p.out_stride = out_stride;
-    p.ntiles = ntiles_;
+    // Tiles [0, nbox) are BOX tiles.  When only a few tiles are GATHER/EMPTY they ride along
+    // in the TMA ring (one launch; their global latency hides among the BOX tiles); when
+    // they are many (strong minification, big unmapped borders) they go to the gather
+    // kernel K3, which hides that latency with plain parallelism.
+    const bool split = (ntiles_ - nbox_tiles_) * 100u > ntiles_ * static_cast<uint32_t>(split_percent_);
+    const uint32_t ring_tiles = split ? nbox_tiles_ : ntiles_;
+    p.ntiles = ring_tiles;
     p.nframes = static_cast<uint32_t>(nframes);
-    p.total = ntiles_ * static_cast<uint32_t>(nframes);
+    p.total = ring_tiles * static_cast<uint32_t>(nframes);
     p.width = width_;
     p.height = height_;
     const bool rubix = rubix_;
@@ -702,15 +868,29 @@ bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_o
     }
     uint32_t grid = static_cast<uint32_t>(sm_count_ * tiled_ctas_per_sm_[vi]);
     if (grid > p.total) grid = p.total;
-    if (rubix && rgba) warp_tiled_kernel<true, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-    else if (rubix) warp_tiled_kernel<true, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-    else if (rgba) warp_tiled_kernel<false, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-    else warp_tiled_kernel<false, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-    char buf[200];
-    snprintf(buf, sizeof buf, "warp_tiled_kernel<rubix=%d,rgba=%d> grid=%u block=%d (%d CTAs/SM, persistent, %d-stage TMA ring)", rubix, rgba, grid,
-             kTiledThreads, tiled_ctas_per_sm_[vi], kStages);
+    char buf[320];
+    int n = 0;
+    if (p.total > 0) {
+        if (rubix && rgba) warp_tiled_kernel<true, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+        else if (rubix) warp_tiled_kernel<true, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+        else if (rgba) warp_tiled_kernel<false, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+        else warp_tiled_kernel<false, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
+        ++launches_;
+        n = snprintf(buf, sizeof buf, "warp_tiled_kernel<rubix=%d,rgba=%d> grid=%u block=%d (%d CTAs/SM, persistent, %d-stage TMA ring)", rubix, rgba,
+                     grid, kTiledThreads, tiled_ctas_per_sm_[vi], kStages);
+    }
+    const uint32_t nother = ntiles_ - ring_tiles;
+    if (nother > 0) {
+        dim3 g2(nother, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
+        if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else if (rubix) warp_tile_gather_kernel<true, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else if (rgba) warp_tile_gather_kernel<false, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else warp_tile_gather_kernel<false, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        ++launches_;
+        snprintf(buf + n, sizeof buf - static_cast<size_t>(n), "%swarp_tile_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", n ? " + " : "", rubix, rgba,
+                 g2.x, g2.y, kThreads);
+    }
     last_kernel_ = buf;
-    ++launches_;
     CK(cudaGetLastError());
     return true;
 }

@@ -87,7 +87,8 @@ private:
     bool plan_has_box_ = false;
     void *d_tiles_ = nullptr;       // TileDesc[]
     uint8_t *d_entries_ = nullptr;
-    uint32_t ntiles_ = 0;
+    uint32_t ntiles_ = 0, nbox_tiles_ = 0;
+    int split_percent_ = 12;  // GATHER+EMPTY share of tiles above which they get their own kernel
     std::vector<uint16_t> shapes_;
     std::vector<TmapSet *> tmap_sets_;   // small cache keyed by (faces ptr, stride, nframes)
     void *encode_fn_ = nullptr;          // cuTensorMapEncodeTiled

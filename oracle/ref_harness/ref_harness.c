@@ -25,187 +25,19 @@
 
 #include "fisheye.c" /* the reference, in place (engine/NQ/fisheye.c) */
 
-/* ------------------------------------------------------------------------ */
-/* engine data the fisheye layer reads                                       */
-/* ------------------------------------------------------------------------ */
-viddef_t vid;
-vrect_t scr_vrect;
-refdef_t r_refdef;
-int sb_lines = 0;
-byte *host_basepal;
-char com_basedir[MAX_OSPATH];
-cmd_source_t cmd_source;
-static short LittleShort_impl(short l) { return l; }
-short (*LittleShort)(short l) = LittleShort_impl;
+#include "engine_stubs.inc"
 
-static byte g_palette[768];
-
-/* ------------------------------------------------------------------------ */
-/* console                                                                   */
-/* ------------------------------------------------------------------------ */
-static char g_log[1 << 16];
-static size_t g_log_len;
-
-void Con_Printf(const char *fmt, ...)
+static int harness_displayed_plate(int k, int *platesize)
 {
-    va_list ap;
-    va_start(ap, fmt);
-    if (g_log_len < sizeof(g_log) - 1) {
-        int n = vsnprintf(g_log + g_log_len, sizeof(g_log) - g_log_len, fmt, ap);
-        if (n > 0) {
-            g_log_len += (size_t)n;
-            if (g_log_len > sizeof(g_log) - 1) g_log_len = sizeof(g_log) - 1;
-        }
-    }
-    va_end(ap);
-}
-
-void Sys_Error(const char *error, ...)
-{
-    va_list ap;
-    va_start(ap, error);
-    vfprintf(stderr, error, ap);
-    va_end(ap);
-    fputc('\n', stderr);
-    abort();
-}
-
-/* ------------------------------------------------------------------------ */
-/* cmd                                                                       */
-/* ------------------------------------------------------------------------ */
-#define MAX_CMDS 64
-static struct { const char *name; xcommand_t fn; } g_cmds[MAX_CMDS];
-static int g_ncmds;
-static int g_argc;
-static char g_argv_store[16][256];
-static char g_unhandled[4096]; /* commands executed but not registered (e.g. "bind ...") */
-
-void Cmd_AddCommand(const char *cmd_name, xcommand_t function)
-{
-    if (g_ncmds < MAX_CMDS) {
-        g_cmds[g_ncmds].name = cmd_name;
-        g_cmds[g_ncmds].fn = function;
-        g_ncmds++;
-    }
-}
-void Cmd_SetCompletion(const char *cmd_name, cmd_arg_f completion) { (void)cmd_name; (void)completion; }
-int Cmd_Argc(void) { return g_argc; }
-const char *Cmd_Argv(int arg) { return (arg >= 0 && arg < g_argc) ? g_argv_store[arg] : ""; }
-
-/* Tokenise like Quake's COM_Parse: whitespace separated, "quoted strings" kept whole. */
-static void tokenize(const char *text)
-{
-    g_argc = 0;
-    const char *p = text;
-    while (*p && g_argc < 16) {
-        while (*p == ' ' || *p == '\t') p++;
-        if (!*p || *p == '\n' || *p == ';') break;
-        char *out = g_argv_store[g_argc];
-        size_t n = 0;
-        if (*p == '"') {
-            p++;
-            while (*p && *p != '"' && n < 255) out[n++] = *p++;
-            if (*p == '"') p++;
-        } else {
-            while (*p && *p != ' ' && *p != '\t' && *p != '\n' && *p != ';' && n < 255) out[n++] = *p++;
-        }
-        out[n] = 0;
-        g_argc++;
-    }
-}
-
-void Cmd_ExecuteString(const char *text, cmd_source_t src)
-{
-    (void)src;
-    tokenize(text);
-    if (!g_argc) return;
-    for (int i = 0; i < g_ncmds; i++) {
-        if (!strcasecmp(g_cmds[i].name, g_argv_store[0])) {
-            g_cmds[i].fn();
-            return;
-        }
-    }
-    size_t l = strlen(g_unhandled);
-    snprintf(g_unhandled + l, sizeof(g_unhandled) - l, "%s\n", text);
-}
-
-int Q_atoi(const char *str) { return atoi(str); }
-float Q_atof(const char *str) { return (float)atof(str); }
-
-/* ------------------------------------------------------------------------ */
-/* zone / shell / fs                                                         */
-/* ------------------------------------------------------------------------ */
-void *Z_Malloc(int size) { return calloc(1, (size_t)size); }
-static void *g_temp;
-void *Hunk_TempAlloc(int size)
-{
-    free(g_temp);
-    g_temp = calloc(1, (size_t)size);
-    return g_temp;
-}
-void STree_AllocInit(void) {}
-void COM_ScanDir(struct stree_root *root, const char *path, const char *pfx, const char *ext, qboolean stripext)
-{
-    (void)root; (void)path; (void)pfx; (void)ext; (void)stripext;
-}
-static char g_write_dir[MAX_OSPATH] = ".";
-void COM_WriteFile(const char *filename, const void *data, int len)
-{
-    char path[MAX_OSPATH * 2];
-    snprintf(path, sizeof path, "%s/%s", g_write_dir, filename);
-    FILE *f = fopen(path, "wb");
-    if (!f) return;
-    fwrite(data, 1, (size_t)len, f);
-    fclose(f);
-}
-
-/* ------------------------------------------------------------------------ */
-/* renderer                                                                  */
-/* ------------------------------------------------------------------------ */
-static const byte *g_faces;      /* [numplates][ps][ps] supplied by the caller */
-static const byte *g_background; /* [vid.height][vid.width] supplied by the caller */
-static int g_render_calls;
-static int g_rendered_plate[MAX_PLATES];
-
-void D_EnableBackBufferAccess(void) {}
-void D_DisableBackBufferAccess(void) {}
-void R_PushDlights(void) {}
-void R_SetVrect(const vrect_t *pvrectin, vrect_t *pvrect, int lineadj)
-{
-    /* the harness keeps scr_vrect == full screen; see ref_set_screen */
-    (void)pvrectin; (void)pvrect; (void)lineadj;
-}
-void R_ViewChanged(vrect_t *pvrect, int lineadj, float aspect) { (void)pvrect; (void)lineadj; (void)aspect; }
-
-/* F_RenderView calls render_plate() only for plates with display != 0, in
- * index order (fisheye.c:764-794), so the k-th call is the k-th displayed plate. */
-void R_RenderView(void)
-{
-    int k = g_render_calls++;
-    int plate = -1, seen = 0;
+    int seen = 0;
+    *platesize = globe.platesize;
     for (int i = 0; i < globe.numplates; i++) {
         if (globe.plates[i].display) {
-            if (seen == k) { plate = i; break; }
+            if (seen == k) return i;
             seen++;
         }
     }
-    if (plate < 0) return;
-    if (k < MAX_PLATES) g_rendered_plate[k] = plate;
-    if (!g_faces) return;
-    int ps = globe.platesize;
-    const byte *src = g_faces + (size_t)plate * ps * ps;
-    for (int y = 0; y < ps; y++)
-        memcpy(vid.buffer + scr_vrect.x + (size_t)(y + scr_vrect.y) * vid.rowbytes, src + (size_t)y * ps, (size_t)ps);
-}
-
-void Draw_TileClear(int x, int y, int w, int h)
-{
-    for (int row = y; row < y + h; row++) {
-        if (g_background)
-            memcpy(vid.buffer + x + (size_t)row * vid.rowbytes, g_background + x + (size_t)row * vid.width, (size_t)w);
-        else
-            memset(vid.buffer + x + (size_t)row * vid.rowbytes, 0, (size_t)w);
-    }
+    return -1;
 }
 
 /* ------------------------------------------------------------------------ */

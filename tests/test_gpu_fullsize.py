@@ -91,3 +91,35 @@ def test_full_size_parity_and_properties(bb, fe, restate, palette, name, W, H, P
     # property 4 — host path == device path at full size
     host = fe.warp_host(faces.reshape(2, -1))
     assert np.array_equal(host[0], want0) and np.array_equal(host[1], want1)
+
+
+def test_ring_pipeline_stress(bb, fe, palette):
+    """16-frame batches launched back to back, every frame checked against torch's own gather.
+    Guards the smem ring: a stage must not be refilled while loads from it are still in flight
+    (an earlier version released stages right behind pending LDS and corrupted entries)."""
+    import torch
+
+    W, H, PS, N = 3840, 2160, 2048, 16
+    for lens, zoom, rubix in (("quincuncial", "f_cover", True), ("panini", "f_fov 180", False)):
+        fe.command("f_globe cube")
+        fe.command(f"f_lens {lens}")
+        fe.command(zoom)
+        fe.set_rubix(rubix)
+        fe.build_lensmap(W, H, PS, max(1, min(64, os.cpu_count() or 1)))
+        idx, tint = fe.lensmap()
+        t_idx = torch.from_numpy(idx.astype(np.int64)).cuda()
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        d_faces = torch.randint(0, 256, (N, 6, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+        pm = torch.from_numpy(np.concatenate([fe.palmaps(), np.arange(256, dtype=np.uint8)[None]])).cuda()
+        t_tint = torch.from_numpy(np.where(tint == 255, 6, tint).astype(np.int64)).cuda()
+        outs = [torch.zeros((N, H, W), dtype=torch.uint8, device="cuda") for _ in range(4)]
+        for o in outs:
+            fe.warp(d_faces, o, nframes=N)
+        torch.cuda.synchronize()
+        for f in range(N):
+            src = d_faces[f].reshape(-1)[t_idx.clamp(min=0)]
+            if rubix:
+                src = pm[t_tint, src.long()]
+            want = torch.where(t_idx >= 0, src, torch.zeros_like(src))
+            for o in outs:
+                assert torch.equal(o[f], want), (lens, f)
