@@ -330,7 +330,6 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps * npix / float(te.item()) / 1e6
-    shown = sum(fe.display())
     fe.free_pinned(h_faces)
     fe.free_pinned(h_out)
 
@@ -377,9 +376,9 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "launch_us": round(launch_s * 1e6, 2),
                          "note": "achieved = (5*W*H + M) bytes/frame x frames per launch / CUDA-event time of the launch"},
-            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": int(shown * PS * PS * F),
+            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": int(fe.upload_bytes_per_frame * F),
                     "d2h_bytes_per_step": int(npix * F), "steps": e2e_steps, "matches_device_path": same,
-                    "how": "blinky_warp_host: pinned host faces -> cudaMemcpyAsync (only plates the lens shows) -> kernel -> "
+                    "how": "blinky_warp_host: pinned host faces -> cudaMemcpy2DAsync (per shown plate, only the texel rectangle the lens samples) -> kernel -> "
                            "cudaMemcpy2DAsync back, 3-slot stream pipeline; wall clock around synchronous calls"},
             "clocks": sampler.summary("sampled by NVML over the timed region plus 1 s of the identical load"),
         }

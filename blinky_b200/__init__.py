@@ -91,6 +91,7 @@ _SIGNATURES = [
     ("blinky_set_background", c_int, [_CTX, c_void_p]),
     ("blinky_warp_device", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
     ("blinky_warp_host", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int]),
+    ("blinky_upload_bytes_per_frame", c_int64, [_CTX]),
     ("blinky_alloc_pinned", c_int, [_CTX, c_size_t, POINTER(c_void_p)]),
     ("blinky_free_pinned", c_int, [_CTX, c_void_p]),
     ("blinky_sync", c_int, [_CTX]),
@@ -259,6 +260,7 @@ class Fisheye:
     mapped_pixels = property(lambda s: int(s._lib.blinky_mapped_pixels(s._ctx)))
     launch_count = property(lambda s: int(s._lib.blinky_launch_count(s._ctx)))
     last_kernel = property(lambda s: s._lib.blinky_last_kernel(s._ctx).decode())
+    upload_bytes_per_frame = property(lambda s: int(s._lib.blinky_upload_bytes_per_frame(s._ctx)))
     plan_summary = property(lambda s: s._lib.blinky_plan_summary(s._ctx).decode())
 
     def plates(self) -> np.ndarray:

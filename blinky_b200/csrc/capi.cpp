@@ -41,6 +41,7 @@ bool upload(blinky_ctx *c) {
     for (int i = 0; i < BLINKY_MAX_PLATES; ++i) {
         memcpy(c->palmaps + i * 256, c->host.plate(i).palette, 256);
         lm.display[i] = i < c->host.numplates() ? c->host.plate(i).display : 0;
+        memcpy(lm.plate_rect[i], c->host.plate_rect(i), sizeof lm.plate_rect[i]);
     }
     lm.palmaps = c->palmaps;
     lm.rubix = c->host.rubix_enabled();
@@ -278,6 +279,16 @@ int blinky_warp_host(blinky_ctx *ctx, const uint8_t *faces_host, size_t face_str
     return ctx->dev->warp_host(faces_host, face_stride, dst_host, dst_frame_stride, dst_rowbytes, x0, y0, nframes, keep_unmapped != 0)
                ? BLINKY_OK
                : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
+
+int64_t blinky_upload_bytes_per_frame(blinky_ctx *ctx) {
+    int64_t n = 0;
+    if (!ctx->host.built()) return 0;
+    for (int i = 0; i < ctx->host.numplates(); ++i) {
+        const int *r = ctx->host.plate_rect(i);
+        if (ctx->host.plate(i).display && r[0] <= r[2] && r[1] <= r[3]) n += static_cast<int64_t>(r[2] - r[0] + 1) * (r[3] - r[1] + 1);
+    }
+    return n;
 }
 
 int blinky_alloc_pinned(blinky_ctx *ctx, size_t bytes, void **out) {

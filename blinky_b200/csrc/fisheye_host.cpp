@@ -1187,6 +1187,11 @@ void FisheyeHost::finish_build() {
     span_off_.assign(static_cast<size_t>(height_px_) + 1, 0);
     spans_.clear();
     int64_t mapped = 0;
+    for (int p = 0; p < kMaxPlates; ++p) {
+        plate_rect_[p][0] = plate_rect_[p][1] = platesize_;
+        plate_rect_[p][2] = plate_rect_[p][3] = -1;
+    }
+    const int ps2 = platesize_ * platesize_;
     for (int y = 0; y < height_px_; ++y) {
         span_off_[static_cast<size_t>(y)] = static_cast<int32_t>(spans_.size() / 2);
         int run_start = -1;
@@ -1197,6 +1202,12 @@ void FisheyeHost::finish_build() {
                 uint32_t t = tint_[at] == 255 ? 7u : static_cast<uint32_t>(tint_[at] & 7);
                 packed_[at] = 0x80000000u | (t << 28) | static_cast<uint32_t>(ix);
                 ++mapped;
+                int *r = plate_rect_[ix / ps2];
+                const int rem = ix % ps2, ty = rem / platesize_, tx = rem % platesize_;
+                if (tx < r[0]) r[0] = tx;
+                if (ty < r[1]) r[1] = ty;
+                if (tx > r[2]) r[2] = tx;
+                if (ty > r[3]) r[3] = ty;
                 if (run_start < 0) run_start = x;
             } else {
                 packed_[at] = 7u << 28;

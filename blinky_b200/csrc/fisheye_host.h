@@ -79,6 +79,8 @@ public:
     const std::vector<uint8_t> &tints() const { return tint_; }
     const std::vector<uint32_t> &packed() const { return packed_; }
     int64_t mapped_pixels() const { return mapped_; }
+    // per plate, the texel rectangle {x0, y0, x1, y1} (inclusive) the lens reads; x0 > x1 = unused plate
+    const int *plate_rect(int plate) const { return plate_rect_[plate]; }
     // per row, the [x0,x1) spans of mapped pixels (for exact "only mapped pixels
     // are written" copy-back, render_lensmap :2413)
     const std::vector<int32_t> &row_span_offsets() const { return span_off_; }
@@ -193,6 +195,7 @@ private:
     std::vector<uint32_t> packed_;
     std::vector<int32_t> span_off_, spans_;
     int64_t mapped_ = 0;
+    int plate_rect_[kMaxPlates][4];
 };
 
 }  // namespace blinky

@@ -1419,6 +1419,17 @@ void make_closure(State &L, Frame &f, const Expr *e, Value &out) {
     out = Value::object(Type::Function, fn);
 }
 
+// If `e` names a variable, returns the variable's storage (no copy, no refcount traffic);
+// otherwise evaluates into `tmp` and returns that.
+inline const Value *operand(State &L, Frame &f, const Expr *e, Value &tmp) {
+    switch (e->k) {
+        case EK::Local: return &slot_ref(f, e->var);
+        case EK::Upval: return &f.fn->upvals[static_cast<size_t>(e->id)]->v;
+        case EK::Global: return &L.global_slot(e->id);
+        default: eval(L, f, e, tmp); return &tmp;
+    }
+}
+
 void eval_args(State &L, Frame &f, const std::vector<Expr *> &list, ValueList &out) {
     size_t n = list.size();
     for (size_t i = 0; i < n; ++i) {
@@ -1491,13 +1502,69 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
         case EK::Global: out = L.global_slot(e->id); return;
         case EK::Paren: eval(L, f, e->l, out); return;
         case EK::Index: {
-            Value obj, key;
-            eval(L, f, e->l, obj);
+            Value tobj, key;
+            const Value *po = operand(L, f, e->l, tobj);
+            if (po->is_table()) {
+                Table *t = static_cast<Table *>(po->obj());
+                Value keep = Value::object(Type::Table, t);  // the key expression may drop the last reference
+                eval(L, f, e->r, key);
+                out = t->get(key);
+                return;
+            }
+            Value obj = *po;
             eval(L, f, e->r, key);
             index_value(L, f, e, obj, key, out);
             return;
         }
-        case EK::Call:
+        case EK::Call: {
+            // numeric fast path: math.* style C functions on number arguments
+            const size_t na = e->list.size();
+            if (na == 1 || na == 2) {
+                Value tf;
+                const Value *pf = operand(L, f, e->l, tf);
+                if (pf->is_function()) {
+                    const Function *fn = static_cast<const Function *>(pf->obj());
+                    const Expr *a0 = e->list[0];
+                    if (na == 1 && fn->fast1 && a0->k != EK::Call && a0->k != EK::Method && a0->k != EK::Vararg) {
+                        double (*fp)(double) = fn->fast1;
+                        Value ta;
+                        const Value *pa = operand(L, f, a0, ta);
+                        if (pa->is_number()) {
+                            out = Value(fp(pa->num()));
+                            return;
+                        }
+                        // not a number: take the general route with the value already computed
+                        Value fv = *pf, av = *pa;
+                        ValueList rets;
+                        call_value(L, fv, &av, 1, rets, &f, e->line);
+                        if (rets.size() > 0) out = rets[0]; else out = Value();
+                        return;
+                    }
+                    const Expr *a1 = na == 2 ? e->list[1] : nullptr;
+                    if (na == 2 && fn->fast2 && a1->k != EK::Call && a1->k != EK::Method && a1->k != EK::Vararg) {
+                        double (*fp)(double, double) = fn->fast2;
+                        Value fv = *pf;  // arguments may reassign the callee variable
+                        Value ta, tb;
+                        const Value *pa = operand(L, f, a0, ta);
+                        Value av = *pa;
+                        const Value *pb = operand(L, f, a1, tb);
+                        if (av.is_number() && pb->is_number()) {
+                            out = Value(fp(av.num(), pb->num()));
+                            return;
+                        }
+                        Value args2[2] = {av, *pb};
+                        ValueList rets;
+                        call_value(L, fv, args2, 2, rets, &f, e->line);
+                        if (rets.size() > 0) out = rets[0]; else out = Value();
+                        return;
+                    }
+                }
+            }
+            ValueList rets;
+            eval_call(L, f, e, rets);
+            if (rets.size() > 0) out = rets[0]; else out = Value();
+            return;
+        }
         case EK::Method: {
             ValueList rets;
             eval_call(L, f, e, rets);
@@ -1506,13 +1573,19 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
         }
         case EK::Function: make_closure(L, f, e, out); return;
         case EK::Add: case EK::Sub: case EK::Mul: case EK::Div: case EK::Mod: case EK::Pow: {
-            Value a, b;
-            eval(L, f, e->l, a);
-            eval(L, f, e->r, b);
-            if (a.is_number() && b.is_number()) {
-                out = Value(do_arith(e->k, a.num(), b.num()));
+            Value ta, tb;
+            // left operand first, then right (evaluation order is observable through calls)
+            const Value *pa = operand(L, f, e->l, ta);
+            double x0 = 0;
+            const bool a_num = pa->is_number();
+            if (a_num) x0 = pa->num();  // read now: the right operand may assign the variable
+            else if (pa != &ta) ta = *pa;
+            const Value *pb = operand(L, f, e->r, tb);
+            if (a_num && pb->is_number()) {
+                out = Value(do_arith(e->k, x0, pb->num()));
                 return;
             }
+            Value a = a_num ? Value(x0) : ta, b = *pb;
             double x, y;
             if (!coerce_num(a, &x)) {
                 std::string what = describe(e->l, f);
@@ -1550,8 +1623,31 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
         }
         case EK::Lt: case EK::Le: case EK::Gt: case EK::Ge: {
             Value a, b;
-            eval(L, f, e->l, a);
-            eval(L, f, e->r, b);
+            {
+                Value ta, tb;
+                const Value *pa = operand(L, f, e->l, ta);
+                if (pa->is_number()) {
+                    const double x0 = pa->num();
+                    const Value *pb = operand(L, f, e->r, tb);
+                    if (pb->is_number()) {
+                        const double y0 = pb->num();
+                        bool r;
+                        switch (e->k) {
+                            case EK::Lt: r = x0 < y0; break;
+                            case EK::Le: r = x0 <= y0; break;
+                            case EK::Gt: r = y0 < x0; break;
+                            default: r = y0 <= x0; break;
+                        }
+                        out = Value::boolean(r);
+                        return;
+                    }
+                    a = Value(x0);
+                    b = *pb;
+                } else {
+                    a = *pa;
+                    eval(L, f, e->r, b);
+                }
+            }
             bool r;
             switch (e->k) {
                 case EK::Lt: r = less_than(f, e->line, a, b); break;
@@ -1609,10 +1705,21 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
                 }
             }
             if (!e->list.empty()) {
-                ValueList vals;
-                eval_args(L, f, e->list, vals);
-                t->arr.reserve(static_cast<size_t>(vals.size()));
-                for (int i = 0; i < vals.size(); ++i) t->set_int(static_cast<int64_t>(i) + 1, vals[i]);
+                const size_t n = e->list.size();
+                const Expr *last = e->list[n - 1];
+                const bool multi = last->k == EK::Call || last->k == EK::Method || last->k == EK::Vararg;
+                t->arr.reserve(n);
+                int64_t at = 1;
+                for (size_t i = 0; i + (multi ? 1 : 0) < n; ++i) {
+                    Value v;
+                    eval(L, f, e->list[i], v);
+                    t->set_int(at++, v);
+                }
+                if (multi) {
+                    ValueList vals;
+                    eval_multi(L, f, last, vals);
+                    for (int i = 0; i < vals.size(); ++i) t->set_int(at++, vals[i]);
+                }
             }
             out = tv;
             return;
@@ -2555,6 +2662,36 @@ void State::call(const Value &fn, const Value *args, int nargs, ValueList &out) 
 static void reg(State &L, Table *t, const char *name, CFunction f, void *ud = nullptr) {
     t->set(L.new_string(name), L.new_cfunction(f, ud, name));
 }
+static void reg1(State &L, Table *t, const char *name, CFunction f, double (*fast)(double)) {
+    Value v = L.new_cfunction(f, nullptr, name);
+    static_cast<Function *>(v.obj())->fast1 = fast;
+    t->set(L.new_string(name), v);
+}
+static void reg2(State &L, Table *t, const char *name, CFunction f, double (*fast)(double, double)) {
+    Value v = L.new_cfunction(f, nullptr, name);
+    static_cast<Function *>(v.obj())->fast2 = fast;
+    t->set(L.new_string(name), v);
+}
+// the numeric cores of the math1 wrappers above (must compute exactly what they compute)
+static double f_abs(double x) { return std::fabs(x); }
+static double f_acos(double x) { return std::acos(x); }
+static double f_asin(double x) { return std::asin(x); }
+static double f_atan(double x) { return std::atan(x); }
+static double f_ceil(double x) { return std::ceil(x); }
+static double f_cos(double x) { return std::cos(x); }
+static double f_cosh(double x) { return std::cosh(x); }
+static double f_exp(double x) { return std::exp(x); }
+static double f_floor(double x) { return std::floor(x); }
+static double f_log(double x) { return std::log(x); }
+static double f_log10(double x) { return std::log10(x); }
+static double f_sin(double x) { return std::sin(x); }
+static double f_sinh(double x) { return std::sinh(x); }
+static double f_sqrt(double x) { return std::sqrt(x); }
+static double f_tan(double x) { return std::tan(x); }
+static double f_tanh(double x) { return std::tanh(x); }
+static double f_atan2(double y, double x) { return std::atan2(y, x); }
+static double f_pow(double x, double y) { return std::pow(x, y); }
+static double f_fmod(double x, double y) { return std::fmod(x, y); }
 
 void State::open_libs() {
     register_function("print", b_print);
@@ -2576,32 +2713,32 @@ void State::open_libs() {
 
     Value mv = new_table();
     Table *m = static_cast<Table *>(mv.obj());
-    reg(*this, m, "abs", m_abs);
-    reg(*this, m, "acos", m_acos);
-    reg(*this, m, "asin", m_asin);
-    reg(*this, m, "atan", m_atan);
-    reg(*this, m, "atan2", m_atan2);
-    reg(*this, m, "ceil", m_ceil);
-    reg(*this, m, "cos", m_cos);
-    reg(*this, m, "cosh", m_cosh);
+    reg1(*this, m, "abs", m_abs, f_abs);
+    reg1(*this, m, "acos", m_acos, f_acos);
+    reg1(*this, m, "asin", m_asin, f_asin);
+    reg1(*this, m, "atan", m_atan, f_atan);
+    reg2(*this, m, "atan2", m_atan2, f_atan2);
+    reg1(*this, m, "ceil", m_ceil, f_ceil);
+    reg1(*this, m, "cos", m_cos, f_cos);
+    reg1(*this, m, "cosh", m_cosh, f_cosh);
     reg(*this, m, "deg", m_deg);
-    reg(*this, m, "exp", m_exp);
-    reg(*this, m, "floor", m_floor);
-    reg(*this, m, "fmod", m_fmod);
+    reg1(*this, m, "exp", m_exp, f_exp);
+    reg1(*this, m, "floor", m_floor, f_floor);
+    reg2(*this, m, "fmod", m_fmod, f_fmod);
     reg(*this, m, "frexp", m_frexp);
     reg(*this, m, "ldexp", m_ldexp);
-    reg(*this, m, "log", m_log);
-    reg(*this, m, "log10", m_log10);
+    reg1(*this, m, "log", m_log, f_log);  // one-argument form; log(x, base) has 2 args and takes the general route
+    reg1(*this, m, "log10", m_log10, f_log10);
     reg(*this, m, "max", m_max);
     reg(*this, m, "min", m_min);
     reg(*this, m, "modf", m_modf);
-    reg(*this, m, "pow", m_pow);
+    reg2(*this, m, "pow", m_pow, f_pow);
     reg(*this, m, "rad", m_rad);
-    reg(*this, m, "sin", m_sin);
-    reg(*this, m, "sinh", m_sinh);
-    reg(*this, m, "sqrt", m_sqrt);
-    reg(*this, m, "tan", m_tan);
-    reg(*this, m, "tanh", m_tanh);
+    reg1(*this, m, "sin", m_sin, f_sin);
+    reg1(*this, m, "sinh", m_sinh, f_sinh);
+    reg1(*this, m, "sqrt", m_sqrt, f_sqrt);
+    reg1(*this, m, "tan", m_tan, f_tan);
+    reg1(*this, m, "tanh", m_tanh, f_tanh);
     // one RNG per State, leaked deliberately small (freed with the process)
     Rng *rng = new Rng();
     reg(*this, m, "random", m_random, rng);
@@ -2680,6 +2817,8 @@ struct Cloner {
                 Value fv = Value::object(Type::Function, fn);
                 map.emplace(v.obj(), fn);
                 fn->cfn = src->cfn;
+                fn->fast1 = src->fast1;
+                fn->fast2 = src->fast2;
                 fn->ud = src->ud;
                 fn->cname = src->cname;
                 fn->proto = src->proto;

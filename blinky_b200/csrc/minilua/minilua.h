@@ -237,6 +237,11 @@ struct Box : Object {
 struct Function : Object {
     // C function
     CFunction cfn = nullptr;
+    // optional numeric fast paths (math.*): one or two numbers in, one number out.  The
+    // evaluator calls these directly when every argument already is a number, skipping
+    // the argument/result lists; semantics are identical to going through `cfn`.
+    double (*fast1)(double) = nullptr;
+    double (*fast2)(double, double) = nullptr;
     void *ud = nullptr;
     const char *cname = nullptr;
     // Lua closure

@@ -664,6 +664,7 @@ bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
     npix_pad_ = npad;
     rubix_ = lm.rubix;
     memcpy(display_, lm.display, sizeof display_);
+    memcpy(plate_rect_, lm.plate_rect, sizeof plate_rect_);
     span_off_.assign(lm.span_off, lm.span_off + lm.height + 1);
     spans_.assign(lm.spans, lm.spans + lm.nspans * 2);
     have_lensmap_ = true;
@@ -1010,16 +1011,23 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
         Slot &s = *slots_[static_cast<size_t>(f) % slots_.size()];
         finalize_slot(s);  // frees the slot (waits for frame f-3)
         const uint8_t *src = faces_host + static_cast<size_t>(f) * face_stride;
-        // only plates the lens actually looks at are uploaded (display flags, :764-766)
+        // Only what the lens looks at is uploaded: plates with display != 0 (:764-766), and of
+        // those only the texel rectangle the lensmap samples.  (TMA boxes may overhang the
+        // rectangle; those texels are staged but never referenced by an entry.)
         for (int pl = 0; pl < numplates_; ++pl) {
             if (!display_[pl]) continue;
-            const uint8_t *from = src + pl * ps2;
+            const int *r = plate_rect_[pl];
+            if (r[0] > r[2] || r[1] > r[3]) continue;
+            const size_t rw = static_cast<size_t>(r[2] - r[0] + 1), rh = static_cast<size_t>(r[3] - r[1] + 1);
+            const size_t off = pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + r[0];
+            const uint8_t *from = src + off;
             if (!src_pinned) {
-                memcpy(s.h_faces + pl * ps2, from, ps2);
-                from = s.h_faces + pl * ps2;
+                for (size_t y = 0; y < rh; ++y) memcpy(s.h_faces + off + y * platesize_, from + y * platesize_, rw);
+                from = s.h_faces + off;
             }
-            cudaError_t e = cudaMemcpyAsync(s.d_faces + pl * ps2, from, ps2, cudaMemcpyHostToDevice, s.stream);
-            if (e != cudaSuccess) { ok = fail("cudaMemcpyAsync(H2D faces)", e); break; }
+            cudaError_t e = cudaMemcpy2DAsync(s.d_faces + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
+                                              cudaMemcpyHostToDevice, s.stream);
+            if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
         }
         if (!ok) break;
         if (!warp(s.d_faces, slot_face_bytes_, s.d_out, slot_out_bytes_, 1, s.stream, false)) { ok = false; break; }
@@ -1051,6 +1059,15 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
         if (e != cudaSuccess) ok = fail("warp_host", e);
     }
     return ok;
+}
+
+size_t WarpDevice::upload_bytes_per_frame() const {
+    size_t n = 0;
+    for (int pl = 0; pl < numplates_; ++pl) {
+        const int *r = plate_rect_[pl];
+        if (display_[pl] && r[0] <= r[2] && r[1] <= r[3]) n += static_cast<size_t>(r[2] - r[0] + 1) * static_cast<size_t>(r[3] - r[1] + 1);
+    }
+    return n;
 }
 
 bool WarpDevice::alloc_pinned(size_t bytes, void **out) {

@@ -20,6 +20,7 @@ struct LensmapUpload {
     const uint32_t *packed = nullptr;        // [height*width]
     const uint8_t *palmaps = nullptr;        // [6*256]
     int display[6] = {0, 0, 0, 0, 0, 0};
+    int plate_rect[6][4] = {};               // texel rectangle each plate is sampled in (x0,y0,x1,y1)
     bool rubix = false;
     const int32_t *span_off = nullptr;       // [height+1]
     const int32_t *spans = nullptr;          // pairs
@@ -54,6 +55,7 @@ public:
     bool sync();
 
     int64_t launches() const { return launches_; }
+    size_t upload_bytes_per_frame() const;
     const std::string &last_kernel() const { return last_kernel_; }
 
 private:
@@ -71,6 +73,7 @@ private:
     int width_ = 0, height_ = 0, platesize_ = 0, numplates_ = 0;
     size_t npix_ = 0, npix_pad_ = 0;
     int display_[6] = {0, 0, 0, 0, 0, 0};
+    int plate_rect_[6][4] = {};
     bool rubix_ = false;
     bool have_lensmap_ = false;
     uint32_t *d_lensmap_ = nullptr;

@@ -187,6 +187,10 @@ int blinky_warp_device(blinky_ctx *ctx, const void *d_faces, size_t face_stride,
 int blinky_warp_host(blinky_ctx *ctx, const uint8_t *faces_host, size_t face_stride, uint8_t *dst_host,
                      size_t dst_frame_stride, int dst_rowbytes, int x0, int y0, int nframes, int keep_unmapped);
 
+/* bytes blinky_warp_host copies host->device per frame for the current lensmap: for
+ * every plate the lens shows, the texel rectangle it samples */
+int64_t blinky_upload_bytes_per_frame(blinky_ctx *ctx);
+
 /* pinned host memory helpers for callers that want zero staging copies */
 int blinky_alloc_pinned(blinky_ctx *ctx, size_t bytes, void **out);
 int blinky_free_pinned(blinky_ctx *ctx, void *ptr);
