@@ -355,7 +355,9 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         alg_bytes = (5 * npix + M) * F  # 4 B lensmap entry + 1 B source (mapped) + 1 B output per pixel
-        launch_s = elapsed / max(1, launches)
+        # a step is one launch of K2, plus one of K3 when the plan was split: the roofline is
+        # taken over the whole step (all kernels that together warp the batch)
+        launch_s = elapsed / args.steps
         achieved = alg_bytes / launch_s / 1e9
         traffic = None
         try:
@@ -375,7 +377,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "launch_us": round(launch_s * 1e6, 2),
-                         "note": "achieved = (5*W*H + M) bytes/frame x frames per launch / CUDA-event time of the launch"},
+                         "kernels_per_step": int(launches // max(1, args.steps)),
+                         "note": "achieved = (5*W*H + M) bytes/frame x frames per step / CUDA-event time of the step "
+                                 "(K2 tiled kernel, plus K3 gather kernel when the tile plan is split)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": int(fe.upload_bytes_per_frame * F),
                     "d2h_bytes_per_step": int(npix * F), "steps": e2e_steps, "matches_device_path": same,
                     "how": "blinky_warp_host: pinned host faces -> cudaMemcpy2DAsync (per shown plate, only the texel rectangle the lens samples) -> kernel -> "
