@@ -148,7 +148,7 @@ def cpu_baseline(workload, threads_all: bool = False):
             fe.command(f"f_globe {globe}")
             fe.command(f"f_lens {lens}")
             fe.command(zoom)
-            fe.build_lensmap(W, H, PS, os.cpu_count() or 1)
+            fe.build_lensmap(W, H, PS, bb.usable_cpus())
             idx, tint = fe.lensmap()
     O = Restatement()
     pm = O.palmaps(pal)
@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
         with bb.Fisheye(device=None, palette=pal) as fe:
             for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
                 fe.command(c)
-            fe.build_lensmap(W, H, PS, os.cpu_count() or 1)
+            fe.build_lensmap(W, H, PS, bb.usable_cpus())
             idx, tint = fe.lensmap()
         O = Restatement()
         pm = O.palmaps(pal)
@@ -265,7 +265,7 @@ def main():
         fe.command(c)
     fe.set_rubix(rubix)
     t0 = time.time()
-    threads = max(1, min(64, (os.cpu_count() or 1) // max(1, world)))
+    threads = max(1, min(64, bb.usable_cpus() // max(1, world)))
     fe.build_lensmap(W, H, PS, threads)  # every rank rebuilds deterministically: nothing to broadcast
     build_s = time.time() - t0
     fe.set_kernel(args.kernel)
@@ -336,13 +336,16 @@ def main():
     # ---- the final gather to rank 0 (reference topology), timed on its own ---------------
     gather = None
     if world > 1:
+        gathered = gather_frames(d_out, rank, world)  # untimed: NCCL sets its p2p connections up lazily
         barrier()
+        reps = 5
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        gathered = gather_frames(d_out, rank, world)
+        for _ in range(reps):
+            gathered = gather_frames(d_out, rank, world)
         g1.record()
         barrier()
-        tg = torch.tensor([g0.elapsed_time(g1) * 1e-3], dtype=torch.float64, device="cuda")
+        tg = torch.tensor([g0.elapsed_time(g1) * 1e-3 / reps], dtype=torch.float64, device="cuda")
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gsec = float(tg.item())
         gather = {"ms": round(gsec * 1e3, 3), "bytes_into_rank0": (world - 1) * F * npix,

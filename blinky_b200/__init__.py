@@ -369,6 +369,22 @@ class Fisheye:
         self._check(self._lib.blinky_sync(self._ctx))
 
 
+def usable_cpus() -> int:
+    """CPUs this process may really use: the affinity mask capped by the cgroup CPU quota
+    (a container can show 128 CPUs and be throttled to 24)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def synthetic_palette(seed: int = 7) -> np.ndarray:
     """the seeded stand-in for gfx/palette.lmp used by tests and bench"""
     return np.random.default_rng(seed).integers(0, 256, 768, dtype=np.uint8)

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--rubix", action="store_true")
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--threads", type=int, default=os.cpu_count())
+    ap.add_argument("--threads", type=int, default=bb.usable_cpus())
     ap.add_argument("--cold", action="store_true", help="single frame, L2 flushed before every launch")
     ap.add_argument("--kernel", type=int, default=0)
     a = ap.parse_args()

@@ -29,7 +29,7 @@ CONFIGS = [
 def test_full_size_parity_and_properties(bb, fe, restate, palette, name, W, H, PS, globe, lens, zoom, rubix):
     import torch
 
-    threads = max(1, min(64, os.cpu_count() or 1))
+    threads = bb.usable_cpus()
     fe.command(f"f_globe {globe}")
     fe.command(f"f_lens {lens}")
     fe.command(zoom)
@@ -105,7 +105,7 @@ def test_ring_pipeline_stress(bb, fe, palette):
         fe.command(f"f_lens {lens}")
         fe.command(zoom)
         fe.set_rubix(rubix)
-        fe.build_lensmap(W, H, PS, max(1, min(64, os.cpu_count() or 1)))
+        fe.build_lensmap(W, H, PS, bb.usable_cpus())
         idx, tint = fe.lensmap()
         t_idx = torch.from_numpy(idx.astype(np.int64)).cuda()
         gen = torch.Generator(device="cuda").manual_seed(7)
