@@ -354,6 +354,43 @@ def main():
                   "how": "torch.distributed (NCCL) send/recv of each rank's finished uint8 frames to rank 0"}
         if rank == 0:
             assert gathered.shape[0] == world * F
+        # -- fused: every rank's warp kernel stores straight into rank 0's buffer (peer memory over NVLink)
+        frame_bytes = npix
+        base = fe.alloc_device(world * F * frame_bytes) if rank == 0 else 0
+        handle = [fe.ipc_export(base) if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        peer = base if rank == 0 else fe.ipc_open(handle[0])
+        mine = peer + rank * F * frame_bytes
+        for _ in range(3):
+            fe.warp(d_faces, mine, nframes=F, stream=stream)
+        barrier()
+        fsteps = max(5, min(args.steps, 20))
+        f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0e.record()
+        for _ in range(fsteps):
+            fe.warp(d_faces, mine, nframes=F, stream=stream)
+        f1e.record()
+        barrier()
+        tf = torch.tensor([f0e.elapsed_time(f1e) * 1e-3 / fsteps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fsec = float(tf.item())
+        fused_ok = None
+        if rank == 0:
+            # view rank 0's raw gather buffer as a tensor and compare with the NCCL-gathered frames
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (world * F, H, W), "typestr": "|u1", "data": (base, False), "version": 2}
+
+            fused_ok = bool(torch.equal(torch.as_tensor(_Raw(), device="cuda"), gathered))
+        gather.update({"fused_ms_per_step": round(fsec * 1e3, 3), "fused_value": round(world * F * npix / fsec / 1e6, 1),
+                       "fused_matches_nccl_gather": fused_ok,
+                       "fused_how": "warp kernels write their finished frames directly into rank 0's buffer through CUDA-IPC peer "
+                                    "memory (NVLink stores from inside the kernel); no separate collective"})
+        barrier()
+        if rank != 0:
+            fe.ipc_close(peer)
+        barrier()
+        if rank == 0:
+            fe.free_device(base)
 
     if rank == 0:
         peak, peak_src = hbm_peak()

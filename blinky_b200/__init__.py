@@ -94,6 +94,11 @@ _SIGNATURES = [
     ("blinky_upload_bytes_per_frame", c_int64, [_CTX]),
     ("blinky_alloc_pinned", c_int, [_CTX, c_size_t, POINTER(c_void_p)]),
     ("blinky_free_pinned", c_int, [_CTX, c_void_p]),
+    ("blinky_alloc_device", c_int, [_CTX, c_size_t, POINTER(c_void_p)]),
+    ("blinky_free_device", c_int, [_CTX, c_void_p]),
+    ("blinky_ipc_export", c_int, [_CTX, c_void_p, c_void_p]),
+    ("blinky_ipc_open", c_int, [_CTX, c_void_p, POINTER(c_void_p)]),
+    ("blinky_ipc_close", c_int, [_CTX, c_void_p]),
     ("blinky_sync", c_int, [_CTX]),
     ("blinky_set_rgba_table", c_int, [_CTX, c_void_p]),
     ("blinky_warp_device_rgba", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
@@ -360,6 +365,29 @@ class Fisheye:
 
     def free_pinned(self, arr: np.ndarray):
         self._check(self._lib.blinky_free_pinned(self._ctx, arr.ctypes.data))
+
+    # -- peer memory (fused warp + gather) -------------------------------------------------
+    def alloc_device(self, nbytes: int) -> int:
+        p = c_void_p()
+        self._check(self._lib.blinky_alloc_device(self._ctx, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def free_device(self, ptr: int):
+        self._check(self._lib.blinky_free_device(self._ctx, ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = ctypes.create_string_buffer(64)
+        self._check(self._lib.blinky_ipc_export(self._ctx, ptr, ctypes.addressof(h)))
+        return h.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = ctypes.create_string_buffer(handle, 64)
+        p = c_void_p()
+        self._check(self._lib.blinky_ipc_open(self._ctx, ctypes.addressof(h), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.blinky_ipc_close(self._ctx, ptr))
 
     def set_rgba_table(self, table: np.ndarray):
         t = np.ascontiguousarray(table, dtype=np.uint32).reshape(256)

@@ -299,6 +299,26 @@ int blinky_free_pinned(blinky_ctx *ctx, void *ptr) {
     NEED_DEVICE(ctx);
     return ctx->dev->free_pinned(ptr) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
 }
+int blinky_alloc_device(blinky_ctx *ctx, size_t bytes, void **out) {
+    NEED_DEVICE(ctx);
+    return ctx->dev->alloc_device(bytes, out) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
+int blinky_free_device(blinky_ctx *ctx, void *ptr) {
+    NEED_DEVICE(ctx);
+    return ctx->dev->free_device(ptr) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
+int blinky_ipc_export(blinky_ctx *ctx, void *device_ptr, unsigned char handle[64]) {
+    NEED_DEVICE(ctx);
+    return ctx->dev->ipc_export(device_ptr, handle) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
+int blinky_ipc_open(blinky_ctx *ctx, const unsigned char handle[64], void **peer_ptr) {
+    NEED_DEVICE(ctx);
+    return ctx->dev->ipc_open(handle, peer_ptr) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
+int blinky_ipc_close(blinky_ctx *ctx, void *peer_ptr) {
+    NEED_DEVICE(ctx);
+    return ctx->dev->ipc_close(peer_ptr) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());
+}
 int blinky_sync(blinky_ctx *ctx) {
     NEED_DEVICE(ctx);
     return ctx->dev->sync() ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->dev->last_error());

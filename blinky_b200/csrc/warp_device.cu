@@ -515,20 +515,30 @@ __global__ void __launch_bounds__(kThreads) warp_tile_gather_kernel(const TiledP
         bgv[j] = 0;
         if (!(e[j] & BLINKY_LM_VALID) && y < height) bgv[j] = __ldg(p.bg + y * width + x);
     }
-    for (uint32_t f = f0; f < f1; ++f) {
-        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f) * p.face_stride;
-        uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
-        uint32_t v[4];
+    // all gathers of the CTA's frames are issued before the first store: 16 independent
+    // loads in flight per thread instead of 4 (stores may alias loads as far as the compiler
+    // knows, so a plain frame loop would serialise on them)
+    uint32_t v[kGatherFramesPerCta][4];
+#pragma unroll
+    for (int g = 0; g < kGatherFramesPerCta; ++g) {
+        const uint32_t f = f0 + g;
+        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f < f1 ? f : f0) * p.face_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            v[j] = bgv[j];
-            if (e[j] & BLINKY_LM_VALID) v[j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
+            v[g][j] = bgv[j];
+            if (e[j] & BLINKY_LM_VALID) v[g][j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
         }
+    }
+#pragma unroll
+    for (int g = 0; g < kGatherFramesPerCta; ++g) {
+        const uint32_t f = f0 + g;
+        if (f >= f1) break;
+        uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t y = tile_y + warp * 4 + j;
             if (y < height) {
-                uint32_t b = v[j];
+                uint32_t b = v[g][j];
                 if (RUBIX && (e[j] & BLINKY_LM_VALID)) {
                     const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
                     if (t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
@@ -1068,6 +1078,41 @@ size_t WarpDevice::upload_bytes_per_frame() const {
         if (display_[pl] && r[0] <= r[2] && r[1] <= r[3]) n += static_cast<size_t>(r[2] - r[0] + 1) * static_cast<size_t>(r[3] - r[1] + 1);
     }
     return n;
+}
+
+bool WarpDevice::alloc_device(size_t bytes, void **out) {
+    CK(cudaSetDevice(device_));
+    CK(cudaMalloc(out, bytes));
+    return true;
+}
+
+bool WarpDevice::free_device(void *p) {
+    CK(cudaSetDevice(device_));
+    CK(cudaFree(p));
+    return true;
+}
+
+bool WarpDevice::ipc_export(void *p, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaSetDevice(device_));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, 64);
+    return true;
+}
+
+bool WarpDevice::ipc_open(const unsigned char handle[64], void **out) {
+    CK(cudaSetDevice(device_));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));  // maps the peer GPU's memory over NVLink
+    return true;
+}
+
+bool WarpDevice::ipc_close(void *p) {
+    CK(cudaSetDevice(device_));
+    CK(cudaIpcCloseMemHandle(p));
+    return true;
 }
 
 bool WarpDevice::alloc_pinned(size_t bytes, void **out) {

@@ -50,6 +50,11 @@ public:
     bool warp_host(const uint8_t *faces_host, size_t face_stride, uint8_t *dst_host, size_t dst_frame_stride,
                    int dst_rowbytes, int x0, int y0, int nframes, bool keep_unmapped);
 
+    bool alloc_device(size_t bytes, void **out);
+    bool free_device(void *p);
+    bool ipc_export(void *p, unsigned char handle[64]);
+    bool ipc_open(const unsigned char handle[64], void **out);
+    bool ipc_close(void *p);
     bool alloc_pinned(size_t bytes, void **out);
     bool free_pinned(void *p);
     bool sync();

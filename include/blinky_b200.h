@@ -196,6 +196,19 @@ int blinky_alloc_pinned(blinky_ctx *ctx, size_t bytes, void **out);
 int blinky_free_pinned(blinky_ctx *ctx, void *ptr);
 int blinky_sync(blinky_ctx *ctx);
 
+/* ---- peer memory: fused warp + gather over NVLink ------------------------------
+ * The kernels write through whatever device-accessible pointer d_out is.  To fuse the
+ * reference topology's final gather into the warp, rank 0 allocates the gather buffer,
+ * exports it, every other rank (one process per GPU) opens it and passes
+ * `peer_base + its frame offset` as d_out: finished pixels then travel to rank 0 as
+ * NVLink stores issued by the warp kernel itself, no separate collective.
+ * handle: 64 opaque bytes (cudaIpcMemHandle_t), moved between processes by the caller. */
+int blinky_alloc_device(blinky_ctx *ctx, size_t bytes, void **out);
+int blinky_free_device(blinky_ctx *ctx, void *ptr);
+int blinky_ipc_export(blinky_ctx *ctx, void *device_ptr, unsigned char handle[64]);
+int blinky_ipc_open(blinky_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
+int blinky_ipc_close(blinky_ctx *ctx, void *peer_ptr);
+
 /* Fused 8-bit -> 32-bit palette expansion (engine/common/vid_sdl.c:539-546,
  * d_8to24table): same warp, output one uint32 per pixel.  table: 256 entries. */
 int blinky_set_rgba_table(blinky_ctx *ctx, const uint32_t table[256]);
