@@ -87,6 +87,8 @@ _SIGNATURES = [
     ("blinky_lens_inverse", c_int, [_CTX, c_double, c_double, POINTER(c_double)]),
     ("blinky_lens_forward", c_int, [_CTX, c_double, c_double, c_double, POINTER(c_double), POINTER(c_double)]),
     ("blinky_write_config", c_int, [_CTX, c_void_p, c_size_t]),
+    ("blinky_saveglobe_pending", c_int, [_CTX]),
+    ("blinky_save_globe", c_int, [_CTX, c_void_p, c_char_p]),
     ("blinky_set_kernel", c_int, [_CTX, c_int]),
     ("blinky_set_background", c_int, [_CTX, c_void_p]),
     ("blinky_warp_device", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
@@ -314,6 +316,14 @@ class Fisheye:
         buf = ctypes.create_string_buffer(n + 1)
         self._lib.blinky_write_config(self._ctx, ctypes.addressof(buf), n + 1)
         return buf.value.decode()
+
+    @property
+    def saveglobe_pending(self) -> bool:
+        return bool(self._lib.blinky_saveglobe_pending(self._ctx))
+
+    def save_globe(self, faces: np.ndarray, directory: str):
+        f = np.ascontiguousarray(faces, dtype=np.uint8)
+        self._check(self._lib.blinky_save_globe(self._ctx, f.ctypes.data, directory.encode()))
 
     # -- hot path (GPU only) --------------------------------------------------------
     def set_kernel(self, variant: int):

@@ -245,6 +245,14 @@ int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize) {
     return static_cast<int>(s.size());
 }
 
+int blinky_saveglobe_pending(blinky_ctx *ctx) { return ctx->host.saveglobe_pending() ? 1 : 0; }
+int blinky_save_globe(blinky_ctx *ctx, const uint8_t *faces_host, const char *directory) {
+    if (!faces_host) return set_err(ctx, BLINKY_E_INVALID, "faces is NULL");
+    if (!ctx->host.built()) return set_err(ctx, BLINKY_E_STATE, "no lensmap built (plate size unknown)");
+    return ctx->host.save_globe(faces_host, directory ? directory : "") ? BLINKY_OK
+                                                                        : set_err(ctx, BLINKY_E_INVALID, "could not write a PCX file");
+}
+
 // ---- GPU-only entry points: no CPU fallback, fail loudly ------------------
 
 #define NEED_DEVICE(ctx)                                                                                              \

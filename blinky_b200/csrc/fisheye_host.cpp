@@ -493,8 +493,14 @@ bool FisheyeHost::command(const std::string &line) {
         }
         return true;
     }
-    if (ieq(c, "f_saveglobe")) {  // :1120-1136 — PCX export is outside the warp path
-        print("f_saveglobe: globe export is not part of the B200 warp path\n");
+    if (ieq(c, "f_saveglobe")) {  // cmd_saveglobe :1120-1136
+        if (argc < 2) {
+            print("f_saveglobe <name> [full flag=0]: screenshot the globe plates\n");
+            return true;
+        }
+        save_name_ = argv[1].substr(0, 31);
+        save_with_margins_ = argc >= 3 ? q_atoi(argv[2]) : 0;
+        save_pending_ = true;
         return true;
     }
     return false;
@@ -558,6 +564,79 @@ std::string FisheyeHost::write_config() const {
         default: break;
     }
     return out;
+}
+
+// ---------------------------------------------------------------------------
+// globe export (fisheye.c:1396-1486)
+// ---------------------------------------------------------------------------
+
+std::vector<uint8_t> FisheyeHost::plate_pcx(const uint8_t *faces, int plate, bool with_margins) {
+    const int ps = platesize_;
+    std::vector<uint8_t> out(128, 0);  // pcx_t header (engine/NQ/client.h:377-391), zero-filled
+    auto put16 = [&](size_t at, int v) {
+        out[at] = static_cast<uint8_t>(v & 0xff);
+        out[at + 1] = static_cast<uint8_t>((v >> 8) & 0xff);
+    };
+    out[0] = 0x0a;  // manufacturer
+    out[1] = 5;     // version: 256 colours
+    out[2] = 1;     // encoding
+    out[3] = 8;     // bits per pixel
+    put16(8, ps - 1);   // xmax
+    put16(10, ps - 1);  // ymax
+    put16(12, ps);      // hres
+    put16(14, ps);      // vres
+    out[65] = 1;        // colour planes
+    put16(66, ps);      // bytes per line
+    put16(68, 2);       // palette type
+    Worker w;
+    w.L = lua_.get();
+    w.globe_plate = fn_globe_plate_;
+    w.has_globe_plate = fn_globe_plate_.is_function();
+    const uint8_t *data = faces + static_cast<size_t>(plate) * ps * ps;
+    out.reserve(128 + static_cast<size_t>(ps) * ps * 2 + 769);
+    for (int i = 0; i < ps; ++i) {
+        double v = static_cast<double>(i) / ps;
+        for (int j = 0; j < ps; ++j) {
+            double u = static_cast<double>(j) / ps;
+            uint8_t col = *data++;
+            if (!with_margins) {
+                float ray[3];
+                plate_uv_to_ray(plate, u, v, ray);
+                int owner;
+                try {
+                    owner = ray_to_plate_index(w, ray);
+                } catch (LuaError &) {
+                    owner = -1;
+                }
+                if (owner != plate) col = 0xFE;
+            }
+            if ((col & 0xc0) == 0xc0) out.push_back(0xc1);  // escape, as the reference's "uncompressed" RLE does
+            out.push_back(col);
+        }
+    }
+    out.push_back(0x0c);
+    out.insert(out.end(), basepal_, basepal_ + 768);
+    return out;
+}
+
+bool FisheyeHost::save_globe(const uint8_t *faces, const std::string &dir) {
+    save_pending_ = false;
+    bool ok = true;
+    for (int i = 0; i < numplates_; ++i) {
+        char name[64];
+        snprintf(name, sizeof name, "%s%d.pcx", save_name_.c_str(), i);
+        std::vector<uint8_t> pcx = plate_pcx(faces, i, save_with_margins_ != 0);
+        std::string path = dir.empty() ? std::string(name) : dir + "/" + name;
+        FILE *f = fopen(path.c_str(), "wb");
+        if (f) {
+            fwrite(pcx.data(), 1, pcx.size(), f);
+            fclose(f);
+        } else {
+            ok = false;
+        }
+        print("Wrote %s\n", name);
+    }
+    return ok;
 }
 
 // ---------------------------------------------------------------------------

@@ -106,6 +106,15 @@ public:
     double rubix_pad() const { return rubix_pad_; }
     std::string write_config() const;  // F_WriteConfig :683-696
 
+    // f_saveglobe (:1120-1136, 1396-1486): the command only arms a request; the frame
+    // driver hands the plates over once they are rendered
+    bool saveglobe_pending() const { return save_pending_; }
+    // PCX image of one plate exactly as WritePCXplate builds it (texels another plate
+    // owns are blanked to 0xFE unless with_margins)
+    std::vector<uint8_t> plate_pcx(const uint8_t *faces, int plate, bool with_margins);
+    // writes <dir>/<name><i>.pcx for every plate, prints "Wrote ..." and disarms the request
+    bool save_globe(const uint8_t *faces, const std::string &dir);
+
     // raw script probes: 1 = values, 0 = nil, -1 = bad return, -2 = no such function, -3 = script error
     int lens_inverse(double x, double y, double out[3]);
     int lens_forward(double rx, double ry, double rz, double *x, double *y);
@@ -184,6 +193,9 @@ private:
     int rubix_numcells_ = 0;
     double rubix_cell_ = 0, rubix_pad_ = 0;
 
+    bool save_pending_ = false;
+    int save_with_margins_ = 0;
+    std::string save_name_;
     uint8_t basepal_[768];
     bool have_palette_ = false;
 

@@ -19,7 +19,8 @@
  *    instead of being time-sliced over frames (fisheye.c:301-322, 819-826);
  *  - globe.pixels lives in pinned host memory so plates upload with
  *    cudaMemcpyAsync; only plates the lens looks at are uploaded;
- *  - f_saveglobe (PCX export) is not provided.
+ *  - f_saveglobe writes the PCX files itself (into com_gamedir) instead of going
+ *    through COM_WriteFile.
  */
 #include "bspfile.h"
 #include "client.h"
@@ -234,6 +235,12 @@ void F_RenderView(void)
 
             render_plate(i, platesize, f, r, u);
         }
+    }
+
+    if (blinky_saveglobe_pending(b200)) { /* fisheye.c:797-799 */
+        D_EnableBackBufferAccess();
+        blinky_save_globe(b200, globe_pixels, com_gamedir);
+        D_DisableBackBufferAccess();
     }
 
     Draw_TileClear(0, 0, vid.width, vid.height); /* background for pixels the lens does not map */

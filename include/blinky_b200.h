@@ -22,6 +22,7 @@
  *                                       forward :2126-2338), one shot instead of time-sliced
  *   blinky_warp_*                       render_lensmap :2406-2424 (THE hot loop) on the GPU
  *   blinky_write_config                 F_WriteConfig :683-696
+ *   blinky_save_globe                   save_globe / WritePCXplate :1396-1486
  *
  * Conventions: every function returns BLINKY_OK (0) or a negative BLINKY_E_*
  * code; blinky_last_error() has the message.  Nothing ever calls exit() (the
@@ -163,6 +164,13 @@ int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]);
 int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y);
 /* F_WriteConfig text; returns bytes needed (excluding NUL) */
 int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize);
+
+/* f_saveglobe (fisheye.c:1120-1136, 1396-1486): the console command arms a request;
+ * the frame driver asks blinky_saveglobe_pending() after rendering the plates and then
+ * passes them to blinky_save_globe(), which writes <directory>/<name><i>.pcx per plate
+ * (the reference's COM_WriteFile target is com_gamedir) and prints "Wrote ...". */
+int blinky_saveglobe_pending(blinky_ctx *ctx);
+int blinky_save_globe(blinky_ctx *ctx, const uint8_t *faces_host, const char *directory);
 
 /* ---- hot path ("RenderLensMap") — GPU only ------------------------------- */
 int blinky_set_kernel(blinky_ctx *ctx, int kernel_variant);

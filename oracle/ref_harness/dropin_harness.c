@@ -72,6 +72,7 @@ void dropin_shutdown(void)
     g_inited = 0;
 }
 
+void dropin_set_gamedir(const char *dir) { snprintf(com_gamedir, sizeof com_gamedir, "%s", dir); }
 void dropin_command(const char *text) { Cmd_ExecuteString(text, src_command); }
 const char *dropin_log(void) { return g_log; }
 void dropin_log_clear(void) { g_log_len = 0; g_log[0] = 0; }

@@ -281,3 +281,27 @@ def test_plate_sizes_tma_cannot_address(bb, fe, restate, palette, torch_mod):
     faces = bb.synthetic_faces(6, PS, 0)
     want = restate.render(idx, tint, faces, restate.palmaps(palette), True)
     assert np.array_equal(gpu_warp(torch_mod, fe, faces)[0], want)
+
+
+def test_device_memory_and_ipc_export(bb, fe):
+    """peer-memory plumbing on one GPU: allocate, warp straight into the raw buffer, export a handle
+    (opening it needs a second process: bench.py --gpus 2 does that and checks the bytes)"""
+    import torch
+
+    W, H, PS = 128, 64, 32
+    setup(fe, "cube", "panini", W, H, PS)
+    ptr = fe.alloc_device(2 * W * H)
+    handle = fe.ipc_export(ptr)
+    assert len(handle) == 64 and any(handle)
+    faces = np.stack([bb.synthetic_faces(6, PS, f) for f in range(2)])
+    d_faces = torch.from_numpy(faces).cuda()
+    fe.warp(d_faces, ptr, nframes=2)
+    ref_out = torch.zeros((2, H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(d_faces, ref_out, nframes=2)
+    torch.cuda.synchronize()
+
+    class Raw:
+        __cuda_array_interface__ = {"shape": (2, H, W), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    assert torch.equal(torch.as_tensor(Raw(), device="cuda"), ref_out)
+    fe.free_device(ptr)

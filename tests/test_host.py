@@ -307,3 +307,41 @@ def test_rubixgrid_changes_tints_only(host):
     incell = (np.fmod(px / 6.0, 3) >= 1) & (np.fmod(py / 6.0, 3) >= 1)
     assert np.array_equal(t1 != 255, incell)
     host.command("f_rubixgrid 10 4 1")
+
+
+def test_saveglobe_pcx_matches_compiled_reference(bb, host, ref, tmp_path):
+    """f_saveglobe: the PCX files (header, escaped pixel stream, 0xFE blanking of texels another
+    plate owns, palette trailer) must be byte-identical to the reference's WritePCXplate output"""
+    import ctypes
+
+    w, h = 48, 40
+    ps = min(w, h)
+    ref.set_screen(w, h)
+    ref.lib.ref_set_write_dir(str(tmp_path / "ref").encode())
+    os.makedirs(tmp_path / "ref")
+    os.makedirs(tmp_path / "mine")
+    for globe in ("cube", "trism", "fast"):
+        for margins in (0, 1):
+            ref.command(f"f_globe {globe}")
+            ref.command("f_lens equirect")  # shows every plate
+            host.command(f"f_globe {globe}")
+            host.command("f_lens equirect")
+            faces = bb.synthetic_faces(ref.numplates, ps, 6)
+            ref.command(f"f_saveglobe g{margins}_ {margins}")
+            host.command(f"f_saveglobe g{margins}_ {margins}")
+            ref.clear_log()
+            host.clear_log()
+            ref.frame(faces, bb.synthetic_background(w, h))  # F_RenderView: renders plates, then save_globe()
+            host.build_lensmap(w, h, ps)
+            assert host.saveglobe_pending
+            host.save_globe(faces, str(tmp_path / "mine"))
+            assert not host.saveglobe_pending
+            assert ref.log == host.log  # "Wrote <name>" lines
+            for i in range(ref.numplates):
+                name = f"g{margins}_{i}.pcx"
+                a = open(tmp_path / "ref" / name, "rb").read()
+                b = open(tmp_path / "mine" / name, "rb").read()
+                assert a == b, (globe, margins, i, len(a), len(b))
+    host.clear_log()
+    host.command("f_saveglobe")
+    assert "f_saveglobe <name> [full flag=0]" in host.log
