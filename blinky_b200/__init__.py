@@ -58,6 +58,8 @@ _SIGNATURES = [
     ("blinky_set_rubixgrid", c_int, [_CTX, c_int, c_double, c_double]),
     ("blinky_build_lensmap", c_int, [_CTX, c_int, c_int, c_int, c_int]),
     ("blinky_needs_rebuild", c_int, [_CTX, c_int, c_int, c_int]),
+    ("blinky_build_info", c_char_p, [_CTX]),
+    ("blinky_compile_lens", c_int, [_CTX, POINTER(c_size_t)]),
     ("blinky_fisheye_enabled", c_int, [_CTX]),
     ("blinky_lens_valid", c_int, [_CTX]),
     ("blinky_globe_valid", c_int, [_CTX]),
@@ -86,6 +88,7 @@ _SIGNATURES = [
     ("blinky_mapped_pixels", c_int64, [_CTX]),
     ("blinky_lens_inverse", c_int, [_CTX, c_double, c_double, POINTER(c_double)]),
     ("blinky_lens_forward", c_int, [_CTX, c_double, c_double, c_double, POINTER(c_double), POINTER(c_double)]),
+    ("blinky_lens_source", c_int, [_CTX, c_int, c_void_p, c_size_t]),
     ("blinky_write_config", c_int, [_CTX, c_void_p, c_size_t]),
     ("blinky_saveglobe_pending", c_int, [_CTX]),
     ("blinky_save_globe", c_int, [_CTX, c_void_p, c_char_p]),
@@ -234,6 +237,17 @@ class Fisheye:
     def build_lensmap(self, width: int, height: int, platesize: int = 0, threads: int = 1):
         self._check(self._lib.blinky_build_lensmap(self._ctx, width, height, platesize, threads))
 
+    @property
+    def build_info(self) -> str:
+        """How the last lensmap was built ("device: ..." or "host ...")."""
+        return self._lib.blinky_build_info(self._ctx).decode()
+
+    def compile_lens(self) -> int:
+        """Translate the current lens to CUDA and compile it with NVRTC; returns the cubin size."""
+        n = c_size_t()
+        self._check(self._lib.blinky_compile_lens(self._ctx, ctypes.byref(n)))
+        return n.value
+
     def needs_rebuild(self, width: int, height: int, platesize: int = 0) -> bool:
         return bool(self._lib.blinky_needs_rebuild(self._ctx, width, height, platesize))
 
@@ -310,6 +324,15 @@ class Fisheye:
         x, y = c_double(), c_double()
         st = self._lib.blinky_lens_forward(self._ctx, rx, ry, rz, ctypes.byref(x), ctypes.byref(y))
         return st, (x.value, y.value)
+
+    def lens_source(self, cuda: bool = False) -> str:
+        """The current ``lens_inverse`` translated to C++/CUDA (raises when not translatable)."""
+        n = self._lib.blinky_lens_source(self._ctx, int(cuda), None, 0)
+        if n < 0:
+            self._check(n)
+        buf = ctypes.create_string_buffer(n + 1)
+        self._lib.blinky_lens_source(self._ctx, int(cuda), ctypes.addressof(buf), n + 1)
+        return buf.value.decode()
 
     def write_config(self) -> str:
         n = self._lib.blinky_write_config(self._ctx, None, 0)

@@ -2,22 +2,32 @@
 // FisheyeHost (host-side scripts/console/lensmap build) and WarpDevice (CUDA).
 #include "../../include/blinky_b200.h"
 
+#include <sched.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
 #include "fisheye_host.h"
+#include "lens_device.h"
 #include "tile_plan.h"
 #include "warp_device.h"
 
 using blinky::FisheyeHost;
+using blinky::LensBuildParams;
+using blinky::LensDevice;
 using blinky::WarpDevice;
 
 struct blinky_ctx {
     FisheyeHost host;
     std::unique_ptr<WarpDevice> dev;
+    std::unique_ptr<LensDevice> lens_dev;
+    std::string build_info;
     std::string err;
     std::string scratch;
     uint8_t palmaps[BLINKY_MAX_PLATES * 256];
@@ -28,6 +38,30 @@ namespace {
 int set_err(blinky_ctx *c, int code, const std::string &msg) {
     c->err = msg;
     return code;
+}
+
+// CPUs this process may really use: the affinity mask, capped by the cgroup CPU quota
+// (a container can see 128 cores and be allowed 24)
+int usable_cpus() {
+    int n = static_cast<int>(std::thread::hardware_concurrency());
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char quota[64];
+        long period = 0;
+        if (fscanf(f, "%63s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+            int q = static_cast<int>((atol(quota) + period - 1) / period);
+            if (q >= 1 && q < n) n = q;
+        }
+        fclose(f);
+    }
+    return n < 1 ? 1 : n;
+}
+
+bool device_lens_builder(void *user, const std::string &src, const LensBuildParams &p, uint32_t *cand, std::string *err) {
+    blinky_ctx *c = static_cast<blinky_ctx *>(user);
+    return c->lens_dev->build(src, p, cand, err);
 }
 
 bool upload(blinky_ctx *c) {
@@ -75,6 +109,8 @@ int blinky_create(int device, blinky_ctx **out) {
     if (device >= 0) {
         try {
             c->dev.reset(new WarpDevice(device));
+            c->lens_dev.reset(new LensDevice(device));
+            c->host.set_device_builder(device_lens_builder, c, usable_cpus());
         } catch (std::exception &e) {
             // no silent CPU fallback: hand back a context that explains itself
             c->err = e.what();
@@ -152,7 +188,14 @@ int blinky_set_rubixgrid(blinky_ctx *ctx, int numcells, double cell, double pad)
 
 int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, int threads) {
     if (width <= 0 || height <= 0) return set_err(ctx, BLINKY_E_INVALID, "width/height must be positive");
+    if (threads < 0) threads = usable_cpus();
     int rc = ctx->host.build_lensmap(width, height, platesize, threads);
+    ctx->build_info = ctx->host.build_info();
+    if (ctx->lens_dev && ctx->build_info.compare(0, 7, "device:") == 0) {
+        char t[96];
+        snprintf(t, sizeof t, "; NVRTC %.0f ms, kernel %.3f ms", ctx->lens_dev->last_compile_ms(), ctx->lens_dev->last_kernel_ms());
+        ctx->build_info += t;
+    }
     // the (possibly empty) map is published even on failure, as the reference renders it
     if (!upload(ctx)) return BLINKY_E_CUDA;
     switch (rc) {
@@ -162,6 +205,18 @@ int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, 
         case -7: return set_err(ctx, BLINKY_E_STATE, "lens or globe is not valid");
         default: return set_err(ctx, BLINKY_E_SCRIPT, "lens script failed during the build: " + ctx->host.log());
     }
+}
+
+const char *blinky_build_info(blinky_ctx *ctx) { return ctx->build_info.c_str(); }
+
+int blinky_compile_lens(blinky_ctx *ctx, size_t *cubin_bytes) {
+    std::string src, why;
+    if (!ctx->host.lens_device_source(true, &src, &why)) return set_err(ctx, BLINKY_E_SCRIPT, why);
+    std::vector<char> cubin;
+    std::string log;
+    if (!LensDevice::compile(src, &cubin, &log)) return set_err(ctx, BLINKY_E_CUDA, log);
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    return BLINKY_OK;
 }
 
 int blinky_needs_rebuild(blinky_ctx *ctx, int w, int h, int ps) { return ctx->host.needs_rebuild(w, h, ps) ? 1 : 0; }
@@ -233,6 +288,17 @@ int64_t blinky_mapped_pixels(blinky_ctx *ctx) { return ctx->host.mapped_pixels()
 int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]) { return ctx->host.lens_inverse(x, y, ray_out); }
 int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y) {
     return ctx->host.lens_forward(rx, ry, rz, x, y);
+}
+
+int blinky_lens_source(blinky_ctx *ctx, int cuda, char *buf, size_t bufsize) {
+    std::string s, why;
+    if (!ctx->host.lens_device_source(cuda != 0, &s, &why)) return set_err(ctx, BLINKY_E_SCRIPT, why);
+    if (buf && bufsize) {
+        size_t n = s.size() < bufsize - 1 ? s.size() : bufsize - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return static_cast<int>(s.size());
 }
 
 int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize) {

@@ -6,6 +6,7 @@
 // float expressions are evaluated in float (x86-64, FLT_EVAL_METHOD 0) and this
 // file is compiled with -ffp-contract=off and never with -ffast-math.
 #include "fisheye_host.h"
+#include "lua_transpile.h"
 
 #include <array>
 #include <atomic>
@@ -828,6 +829,24 @@ int FisheyeHost::call_forward(Worker &w, const float ray[3], double *x, double *
     return -1;
 }
 
+bool FisheyeHost::lens_device_source(bool cuda, std::string *source, std::string *why) {
+    if (!fn_inverse_.is_function()) {
+        *why = "the lens has no lens_inverse";
+        return false;
+    }
+    if (fn_globe_plate_.is_function()) {
+        *why = "the globe selects plates with a script function (globe_plate)";
+        return false;
+    }
+    TranspileResult r = transpile_lens(*lua_, fn_inverse_);
+    if (!r.ok) {
+        *why = r.error;
+        return false;
+    }
+    *source = transpile_prelude(cuda) + r.source;
+    return true;
+}
+
 int FisheyeHost::lens_inverse(double x, double y, double out[3]) {
     if (!fn_inverse_.is_function()) return -2;
     Value args[2] = {Value(x), Value(y)};
@@ -1010,77 +1029,170 @@ int FisheyeHost::build_inverse_rows(Worker &w, int y_begin, int y_end, int *disp
     return 0;
 }
 
-int FisheyeHost::build_inverse(int threads) {
-    if (!fn_inverse_.is_function()) {
-        print("lens_inverse is not a function\n");
-        return -2;
+int FisheyeHost::build_inverse_pixels(Worker &w, const int32_t *pixels, size_t n, int *display) {
+    for (size_t i = 0; i < n; ++i) {
+        const int ly = pixels[i] / width_px_, lx = pixels[i] % width_px_;
+        double y = -(ly - height_px_ / 2) * scale_;
+        double x = (lx - width_px_ / 2) * scale_;
+        float ray[3];
+        int status = call_inverse(w, x, y, ray);
+        if (status == 0) continue;
+        if (status == -1) return -1;
+        set_from_ray(w, lx, ly, ray, display);
     }
-    int display[kMaxPlates] = {0, 0, 0, 0, 0, 0};
+    return 0;
+}
+
+template <class F>
+int FisheyeHost::run_inverse_workers(int threads, int nitems, int *display, F item) {
     int rc = 0;
-    if (threads <= 1) {
+    if (threads <= 1 || nitems <= 1) {
         Worker w;
         w.L = lua_.get();
         w.inverse = fn_inverse_;
         w.globe_plate = fn_globe_plate_;
         w.has_globe_plate = fn_globe_plate_.is_function();
         try {
-            rc = build_inverse_rows(w, 0, height_px_, display);
+            for (int i = 0; i < nitems && rc == 0; ++i) rc = item(w, i, display);
         } catch (LuaError &e) {
             print("%s\n", e.what());
             rc = -1;
         }
-    } else {
-        // Row bands over cloned Lua states.  The handles are parked in globals so
-        // that State::clone() carries them over to each worker.
-        lua_->set_global("__blinky_inverse", fn_inverse_);
-        lua_->set_global("__blinky_globe_plate", fn_globe_plate_);
-        std::vector<Worker> workers(static_cast<size_t>(threads));
-        for (auto &w : workers) {
-            w.owned = lua_->clone();
-            w.L = w.owned.get();
-            w.inverse = w.L->get_global("__blinky_inverse");
-            w.globe_plate = w.L->get_global("__blinky_globe_plate");
-            w.has_globe_plate = w.globe_plate.is_function();
-        }
-        lua_->set_global("__blinky_inverse", Value());
-        lua_->set_global("__blinky_globe_plate", Value());
-        const int band = 8;
-        std::atomic<int> next_band(0);
-        std::atomic<int> failed(0);
-        std::vector<std::array<int, kMaxPlates>> disp(static_cast<size_t>(threads));
-        for (auto &d : disp) d.fill(0);
-        std::vector<std::string> errors(static_cast<size_t>(threads));
-        std::vector<std::thread> pool;
-        const int nbands = (height_px_ + band - 1) / band;
-        for (int t = 0; t < threads; ++t) {
-            pool.emplace_back([&, t]() {
-                Worker &w = workers[static_cast<size_t>(t)];
-                for (;;) {
-                    int b = next_band.fetch_add(1);
-                    if (b >= nbands || failed.load()) break;
-                    int y0 = b * band, y1 = std::min(height_px_, y0 + band);
-                    try {
-                        if (build_inverse_rows(w, y0, y1, disp[static_cast<size_t>(t)].data()) != 0) failed.store(1);
-                    } catch (LuaError &e) {
-                        errors[static_cast<size_t>(t)] = e.what();
-                        failed.store(1);
-                    }
+        return rc;
+    }
+    // Cloned Lua states.  The handles are parked in globals so that State::clone()
+    // carries them over to each worker.
+    lua_->set_global("__blinky_inverse", fn_inverse_);
+    lua_->set_global("__blinky_globe_plate", fn_globe_plate_);
+    std::vector<Worker> workers(static_cast<size_t>(threads));
+    for (auto &w : workers) {
+        w.owned = lua_->clone();
+        w.L = w.owned.get();
+        w.inverse = w.L->get_global("__blinky_inverse");
+        w.globe_plate = w.L->get_global("__blinky_globe_plate");
+        w.has_globe_plate = w.globe_plate.is_function();
+    }
+    lua_->set_global("__blinky_inverse", Value());
+    lua_->set_global("__blinky_globe_plate", Value());
+    std::atomic<int> next_item(0);
+    std::atomic<int> failed(0);
+    std::vector<std::array<int, kMaxPlates>> disp(static_cast<size_t>(threads));
+    for (auto &d : disp) d.fill(0);
+    std::vector<std::string> errors(static_cast<size_t>(threads));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t]() {
+            Worker &w = workers[static_cast<size_t>(t)];
+            for (;;) {
+                int i = next_item.fetch_add(1);
+                if (i >= nitems || failed.load()) break;
+                try {
+                    if (item(w, i, disp[static_cast<size_t>(t)].data()) != 0) failed.store(1);
+                } catch (LuaError &e) {
+                    errors[static_cast<size_t>(t)] = e.what();
+                    failed.store(1);
                 }
-            });
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    // release worker handles before their states die
+    for (auto &w : workers) {
+        w.inverse = Value();
+        w.globe_plate = Value();
+    }
+    for (auto &d : disp)
+        for (int i = 0; i < kMaxPlates; ++i) display[i] |= d[static_cast<size_t>(i)];
+    if (failed.load()) {
+        for (auto &e : errors)
+            if (!e.empty()) print("%s\n", e.c_str());
+        rc = -1;
+    }
+    return rc;
+}
+
+int FisheyeHost::build_inverse_device(int *display, std::string *why) {
+    std::string src;
+    if (!lens_device_source(true, &src, why)) return 1;
+    LensBuildParams p;
+    memset(&p, 0, sizeof p);
+    p.width = width_px_;
+    p.height = height_px_;
+    p.platesize = platesize_;
+    p.numplates = numplates_;
+    p.scale = scale_;
+    // rubix grid geometry exactly as set_from_plate derives it
+    p.rubix_block = rubix_pad_ + rubix_cell_;
+    p.rubix_pad = rubix_pad_;
+    const double units = rubix_numcells_ * p.rubix_block + rubix_pad_;
+    p.rubix_unit_px = static_cast<double>(platesize_) / units;
+    for (int i = 0; i < numplates_; ++i) {
+        const Plate &pl = plates_[i];
+        p.uv_dist[i] = 0.5 / std::tan(static_cast<double>(pl.fov / 2));
+        for (int k = 0; k < 3; ++k) {
+            p.plates[i].forward[k] = pl.forward[k];
+            p.plates[i].right[k] = pl.right[k];
+            p.plates[i].up[k] = pl.up[k];
         }
-        for (auto &th : pool) th.join();
-        // release worker handles before their states die
-        for (auto &w : workers) {
-            w.inverse = Value();
-            w.globe_plate = Value();
+        p.plates[i].dist = pl.dist;
+    }
+    const size_t area = idx_.size();
+    std::vector<uint32_t> cand(area);
+    if (!device_builder_(device_builder_user_, src, p, cand.data(), why)) return 1;
+
+    std::vector<int32_t> undecided;
+    const int ps2 = platesize_ * platesize_;
+    for (size_t at = 0; at < area; ++at) {
+        const uint32_t c = cand[at];
+        if (c & kCandRisk) {
+            undecided.push_back(static_cast<int32_t>(at));
+        } else if (c & kCandValid) {
+            const int32_t ix = static_cast<int32_t>(c & 0x0FFFFFFFu);
+            const int plate = ix / ps2;
+            idx_[at] = ix;
+            display[plate] = 1;
+            if (!(c & kCandOnGrid)) tint_[at] = static_cast<uint8_t>(plate);
         }
-        for (auto &d : disp)
-            for (int i = 0; i < kMaxPlates; ++i) display[i] |= d[static_cast<size_t>(i)];
-        if (failed.load()) {
-            for (auto &e : errors)
-                if (!e.empty()) print("%s\n", e.c_str());
-            rc = -1;
+    }
+    // the interpreter decides what the device could not
+    const int chunk = 256;
+    const int nitems = static_cast<int>((undecided.size() + chunk - 1) / chunk);
+    const int threads = undecided.size() >= 4096 ? fallback_threads_ : 1;
+    int rc = run_inverse_workers(threads, nitems, display, [&](Worker &w, int i, int *disp) {
+        const size_t b = static_cast<size_t>(i) * chunk;
+        return build_inverse_pixels(w, undecided.data() + b, std::min<size_t>(chunk, undecided.size() - b), disp);
+    });
+    char info[160];
+    snprintf(info, sizeof info, "device: %zu of %zu pixels re-evaluated by the interpreter", undecided.size(), area);
+    build_info_ = info;
+    return rc == 0 ? 0 : -1;
+}
+
+int FisheyeHost::build_inverse(int threads) {
+    if (!fn_inverse_.is_function()) {
+        print("lens_inverse is not a function\n");
+        return -2;
+    }
+    int display[kMaxPlates] = {0, 0, 0, 0, 0, 0};
+    int rc = 1;
+    build_info_.clear();
+    if (threads == 0) {
+        std::string why = "no GPU lens builder installed";
+        if (device_builder_) rc = build_inverse_device(display, &why);
+        if (rc == 1) {
+            build_info_ = "host (" + why + ")";
+            threads = fallback_threads_;
         }
+    }
+    if (rc == 1) {
+        if (threads < 1) threads = 1;
+        if (build_info_.empty()) build_info_ = "host";
+        const int band = threads > 1 ? 8 : height_px_;  // one thread: the reference's single bottom-up sweep
+        const int nbands = (height_px_ + band - 1) / band;
+        rc = run_inverse_workers(threads, nbands, display, [&](Worker &w, int b, int *disp) {
+            const int y0 = b * band;
+            return build_inverse_rows(w, y0, std::min(height_px_, y0 + band), disp);
+        });
     }
     for (int i = 0; i < kMaxPlates; ++i) plates_[i].display = display[i];
     return rc;

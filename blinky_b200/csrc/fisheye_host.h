@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "lens_device.h"
 #include "minilua/minilua.h"
 
 namespace blinky {
@@ -63,8 +64,20 @@ public:
     void set_rubixgrid(int numcells, double cell, double pad);
 
     // ---- build -------------------------------------------------------------
-    // returns 0 ok; -2 script problem; -3 zoom failure; -7 invalid lens/globe
+    // returns 0 ok; -2 script problem; -3 zoom failure; -7 invalid lens/globe.
+    // threads >= 1: the lens script is interpreted on that many host threads.
+    // threads == 0: evaluate the lens on the GPU when a device builder is installed and the
+    // lens translates (lua_transpile.h); pixels the device cannot decide exactly, and lenses
+    // outside the translatable subset, go through the interpreter on `fallback_threads`.
     int build_lensmap(int width, int height, int platesize, int threads);
+    using DeviceBuilder = bool (*)(void *user, const std::string &cuda_source, const LensBuildParams &p, uint32_t *cand, std::string *err);
+    void set_device_builder(DeviceBuilder fn, void *user, int fallback_threads) {
+        device_builder_ = fn;
+        device_builder_user_ = user;
+        fallback_threads_ = fallback_threads < 1 ? 1 : fallback_threads;
+    }
+    // one line about how the last lensmap was built ("device: ..." / "host: ...")
+    const std::string &build_info() const { return build_info_; }
     bool needs_rebuild(int width, int height, int platesize) const;
 
     // ---- results -------------------------------------------------------------
@@ -119,6 +132,10 @@ public:
     int lens_inverse(double x, double y, double out[3]);
     int lens_forward(double rx, double ry, double rz, double *x, double *y);
 
+    // C++/CUDA source of the current lens_inverse (lua_transpile.h); false + reason when the
+    // lens is outside the transpilable subset
+    bool lens_device_source(bool cuda, std::string *source, std::string *why);
+
     // pure converters, exposed for the Lua-visible wrappers
     static void latlon_to_ray(double lat, double lon, float ray[3]);
     static void ray_to_latlon(const float ray[3], double *lat, double *lon);
@@ -142,7 +159,12 @@ private:
     int call_inverse(Worker &w, double x, double y, float ray[3]);
     int call_forward(Worker &w, const float ray[3], double *x, double *y);
     int build_inverse_rows(Worker &w, int y_begin, int y_end, int *display);  // rows [y_begin,y_end), bottom-up
+    int build_inverse_pixels(Worker &w, const int32_t *pixels, size_t n, int *display);
+    // runs item(w, i, display) for i in [0, nitems) over `threads` cloned script states
+    template <class F>
+    int run_inverse_workers(int threads, int nitems, int *display, F item);
     int build_inverse(int threads);
+    int build_inverse_device(int *display, std::string *why);  // 0 ok, -1 script failure, 1 = not possible (why)
     int build_forward(int threads);
     int uv_to_screen(Worker &w, int plate, double u, double v, int *lx, int *ly);
     void draw_quad(const int *tl, const int *tr, const int *bl, const int *br, int plate, int px, int py, int *display);
@@ -156,6 +178,11 @@ private:
 
     std::unique_ptr<minilua::State> lua_;
     minilua::Value fn_inverse_, fn_forward_, fn_globe_plate_;  // registry refs, :328-332
+
+    DeviceBuilder device_builder_ = nullptr;
+    void *device_builder_user_ = nullptr;
+    int fallback_threads_ = 1;
+    std::string build_info_;
 
     PrintFn print_fn_ = nullptr;
     void *print_user_ = nullptr;

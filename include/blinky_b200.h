@@ -117,12 +117,26 @@ int blinky_set_rubixgrid(blinky_ctx *ctx, int numcells, double cell_size, double
 /* ---- lensmap build ("InitLensMap") -------------------------------------- */
 /* Builds the lensmap for a width x height view and square plates of
  * `platesize` pixels (the reference forces platesize = min(w,h), :707; pass
- * platesize <= 0 for that behaviour).  threads <= 1 evaluates the lens in the
- * reference's own order on one Lua state; threads > 1 splits rows over cloned
- * Lua states (requires lens_inverse to be a pure function of x,y — true for
- * every shipped lens).  On a GPU context the packed map, tile table and tint
- * LUTs are uploaded too. */
+ * platesize <= 0 for that behaviour).
+ *   threads == 1  the lens script is interpreted in the reference's own order on one
+ *                 script state;
+ *   threads  > 1  rows are split over that many cloned script states (requires
+ *                 lens_inverse to be a pure function of x,y — true for every shipped lens);
+ *   threads  < 0  as above with every CPU the process may use;
+ *   threads == 0  GPU build: lens_inverse is translated to CUDA, compiled for sm_100a
+ *                 with NVRTC and evaluated for all pixels by one kernel; pixels whose
+ *                 result is not provably the host's (error bounds on every libm call)
+ *                 are re-evaluated by the interpreter, so the map is the same as the
+ *                 host build's.  Lenses outside the translatable subset, forward-only
+ *                 lenses and CPU-only contexts fall back to threads < 0.
+ * blinky_build_info() says which way the last build went.
+ * On a GPU context the packed map, tile table and tint LUTs are uploaded too. */
 int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, int threads);
+/* e.g. "device: 12 of 8294400 pixels re-evaluated by the interpreter; NVRTC 310 ms, kernel 1.9 ms"
+ * or "host (line 22: nil values are not supported here)" */
+const char *blinky_build_info(blinky_ctx *ctx);
+/* Translate + NVRTC-compile the current lens without running it (works without a GPU). */
+int blinky_compile_lens(blinky_ctx *ctx, size_t *cubin_bytes);
 /* 1 if a lens/globe/zoom/rubixgrid/size change since the last build requires a rebuild (:730) */
 int blinky_needs_rebuild(blinky_ctx *ctx, int width, int height, int platesize);
 
@@ -162,6 +176,10 @@ int64_t blinky_mapped_pixels(blinky_ctx *ctx);        /* M in the 5*W*H + M byte
  * return 1 = values, 0 = nil, negative = error */
 int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]);
 int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y);
+/* The current lens_inverse translated to C++ (cuda=0) or CUDA C++ (cuda=1) — what the device
+ * lensmap builder compiles.  Returns the bytes needed (excluding NUL), or
+ * BLINKY_E_SCRIPT when the lens is outside the translatable subset (reason: blinky_last_error). */
+int blinky_lens_source(blinky_ctx *ctx, int cuda, char *buf, size_t bufsize);
 /* F_WriteConfig text; returns bytes needed (excluding NUL) */
 int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize);
 
