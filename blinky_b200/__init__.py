@@ -59,6 +59,7 @@ _SIGNATURES = [
     ("blinky_build_lensmap", c_int, [_CTX, c_int, c_int, c_int, c_int]),
     ("blinky_needs_rebuild", c_int, [_CTX, c_int, c_int, c_int]),
     ("blinky_build_info", c_char_p, [_CTX]),
+    ("blinky_plan_digest", ctypes.c_uint64, [_CTX, c_int]),
     ("blinky_compile_lens", c_int, [_CTX, POINTER(c_size_t)]),
     ("blinky_fisheye_enabled", c_int, [_CTX]),
     ("blinky_lens_valid", c_int, [_CTX]),
@@ -241,6 +242,9 @@ class Fisheye:
     def build_info(self) -> str:
         """How the last lensmap was built ("device: ..." or "host ...")."""
         return self._lib.blinky_build_info(self._ctx).decode()
+
+    def plan_digest(self, threads: int = 1) -> int:
+        return int(self._lib.blinky_plan_digest(self._ctx, threads))
 
     def compile_lens(self) -> int:
         """Translate the current lens to CUDA and compile it with NVRTC; returns the cubin size."""

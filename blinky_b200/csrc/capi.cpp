@@ -4,6 +4,7 @@
 
 #include <sched.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,7 +84,7 @@ bool upload(blinky_ctx *c) {
     lm.spans = c->host.row_spans().data();
     lm.nspans = c->host.row_spans().size() / 2;
     // TMA needs 16-byte aligned plate rows; other plate sizes use direct gathers only
-    blinky::TilePlan plan = blinky::make_tile_plan(lm.packed, lm.width, lm.height, lm.platesize, lm.platesize % 16 == 0);
+    blinky::TilePlan plan = blinky::make_tile_plan(lm.packed, lm.width, lm.height, lm.platesize, lm.platesize % 16 == 0, c->host.worker_threads());
     lm.plan = &plan;
     if (!c->dev->upload_lensmap(lm)) {
         c->err = c->dev->last_error();
@@ -106,11 +107,12 @@ int blinky_create(int device, blinky_ctx **out) {
         return BLINKY_E_NOMEM;
     }
     memset(c->palmaps, 0, sizeof c->palmaps);
+    c->host.set_worker_threads(usable_cpus());
     if (device >= 0) {
         try {
             c->dev.reset(new WarpDevice(device));
             c->lens_dev.reset(new LensDevice(device));
-            c->host.set_device_builder(device_lens_builder, c, usable_cpus());
+            c->host.set_device_builder(device_lens_builder, c);
         } catch (std::exception &e) {
             // no silent CPU fallback: hand back a context that explains itself
             c->err = e.what();
@@ -193,11 +195,18 @@ int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, 
     ctx->build_info = ctx->host.build_info();
     if (ctx->lens_dev && ctx->build_info.compare(0, 7, "device:") == 0) {
         char t[96];
-        snprintf(t, sizeof t, "; NVRTC %.0f ms, kernel %.3f ms", ctx->lens_dev->last_compile_ms(), ctx->lens_dev->last_kernel_ms());
+        snprintf(t, sizeof t, " (NVRTC %.0f ms, kernel %.3f ms)", ctx->lens_dev->last_compile_ms(), ctx->lens_dev->last_kernel_ms());
         ctx->build_info += t;
     }
     // the (possibly empty) map is published even on failure, as the reference renders it
-    if (!upload(ctx)) return BLINKY_E_CUDA;
+    auto t0 = std::chrono::steady_clock::now();
+    const bool uploaded = upload(ctx);
+    if (ctx->dev) {
+        char t[64];
+        snprintf(t, sizeof t, ", plan+upload %.1f ms", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        ctx->build_info += t;
+    }
+    if (!uploaded) return BLINKY_E_CUDA;
     switch (rc) {
         case 0: return BLINKY_OK;
         case -1: return set_err(ctx, BLINKY_E_INVALID, "bad size (platesize too large for the 28-bit texel index?)");
@@ -423,6 +432,19 @@ const char *blinky_plan_summary(blinky_ctx *ctx) {
              pl.shapes.size(), pl.n_gather, pl.n_empty, static_cast<double>(pl.entries.size()) / npix);
     ctx->scratch = buf;
     return ctx->scratch.c_str();
+}
+uint64_t blinky_plan_digest(blinky_ctx *ctx, int threads) {
+    if (!ctx->host.built()) return 0;
+    blinky::TilePlan pl = blinky::make_tile_plan(ctx->host.packed().data(), ctx->host.width(), ctx->host.height(),
+                                                 ctx->host.platesize(), ctx->host.platesize() % 16 == 0, threads);
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over the tile table and the entry blocks
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    mix(pl.tiles.data(), pl.tiles.size() * sizeof(blinky::TileDesc));
+    mix(pl.entries.data(), pl.entries.size());
+    return h;
 }
 const char *blinky_last_kernel(blinky_ctx *ctx) { return ctx->dev ? ctx->dev->last_kernel().c_str() : ""; }
 

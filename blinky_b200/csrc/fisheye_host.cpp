@@ -7,9 +7,11 @@
 // file is compiled with -ffp-contract=off and never with -ffast-math.
 #include "fisheye_host.h"
 #include "lua_transpile.h"
+#include "parallel.h"
 
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1141,17 +1143,34 @@ int FisheyeHost::build_inverse_device(int *display, std::string *why) {
     if (!device_builder_(device_builder_user_, src, p, cand.data(), why)) return 1;
 
     std::vector<int32_t> undecided;
-    const int ps2 = platesize_ * platesize_;
-    for (size_t at = 0; at < area; ++at) {
-        const uint32_t c = cand[at];
-        if (c & kCandRisk) {
-            undecided.push_back(static_cast<int32_t>(at));
-        } else if (c & kCandValid) {
-            const int32_t ix = static_cast<int32_t>(c & 0x0FFFFFFFu);
-            const int plate = ix / ps2;
-            idx_[at] = ix;
-            display[plate] = 1;
-            if (!(c & kCandOnGrid)) tint_[at] = static_cast<uint8_t>(plate);
+    {
+        const int ps2 = platesize_ * platesize_;
+        const int rows_per = 16;
+        const int nchunks = (height_px_ + rows_per - 1) / rows_per;
+        std::vector<std::vector<int32_t>> und(static_cast<size_t>(nchunks));
+        std::vector<std::array<int, kMaxPlates>> disp(static_cast<size_t>(nchunks));
+        parallel_for(nchunks, fallback_threads_, [&](int ch) {
+            std::array<int, kMaxPlates> &dp = disp[static_cast<size_t>(ch)];
+            dp.fill(0);
+            const size_t b = static_cast<size_t>(ch) * rows_per * width_px_;
+            const size_t e = std::min(area, b + static_cast<size_t>(rows_per) * width_px_);
+            for (size_t at = b; at < e; ++at) {
+                const uint32_t c = cand[at];
+                if (c & kCandRisk) {
+                    und[static_cast<size_t>(ch)].push_back(static_cast<int32_t>(at));
+                } else if (c & kCandValid) {
+                    const int32_t ix = static_cast<int32_t>(c & 0x0FFFFFFFu);
+                    int plate = 0;
+                    for (int32_t lim = ps2; ix >= lim; lim += ps2) ++plate;  // <= 5 steps, cheaper than a division
+                    idx_[at] = ix;
+                    dp[static_cast<size_t>(plate)] = 1;
+                    if (!(c & kCandOnGrid)) tint_[at] = static_cast<uint8_t>(plate);
+                }
+            }
+        });
+        for (int ch = 0; ch < nchunks; ++ch) {
+            undecided.insert(undecided.end(), und[static_cast<size_t>(ch)].begin(), und[static_cast<size_t>(ch)].end());
+            for (int i = 0; i < kMaxPlates; ++i) display[i] |= disp[static_cast<size_t>(ch)][static_cast<size_t>(i)];
         }
     }
     // the interpreter decides what the device could not
@@ -1175,7 +1194,6 @@ int FisheyeHost::build_inverse(int threads) {
     }
     int display[kMaxPlates] = {0, 0, 0, 0, 0, 0};
     int rc = 1;
-    build_info_.clear();
     if (threads == 0) {
         std::string why = "no GPU lens builder installed";
         if (device_builder_) rc = build_inverse_device(display, &why);
@@ -1341,6 +1359,9 @@ int FisheyeHost::build_lensmap(int width, int height, int platesize, int threads
     built_ = false;
     mapped_ = 0;
 
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+    auto t0 = clk::now();
     // the lens script is run again on every rebuild (:737)
     lens_valid_ = load_lens();
     if (!lens_valid_) {
@@ -1351,24 +1372,41 @@ int FisheyeHost::build_lensmap(int width, int height, int platesize, int threads
     built_w_ = width;
     built_h_ = height;
     built_ps_ = platesize;
+    const double ms_script = ms_since(t0);
 
     int rc = 0;
+    double ms_zoom = 0, ms_map = 0;
+    build_info_.clear();
     if (!lens_valid_ || !globe_valid_) {
         rc = -7;
-    } else if (!calc_zoom()) {
-        rc = -3;
     } else {
-        for (int i = 0; i < numplates_; ++i) plates_[i].display = 0;
-        if (map_type_ == MAP_FORWARD) rc = build_forward(threads) == 0 ? 0 : -2;
-        else if (map_type_ == MAP_INVERSE) rc = build_inverse(threads) == 0 ? 0 : -2;
-        else {
-            print("no inverse or forward map being used\n");
-            rc = -2;
+        t0 = clk::now();
+        const bool zoom_ok = calc_zoom();
+        ms_zoom = ms_since(t0);
+        t0 = clk::now();
+        if (!zoom_ok) {
+            rc = -3;
+        } else {
+            for (int i = 0; i < numplates_; ++i) plates_[i].display = 0;
+            if (map_type_ == MAP_FORWARD) {
+                build_info_ = "host (forward lens)";
+                rc = build_forward(threads) == 0 ? 0 : -2;
+            } else if (map_type_ == MAP_INVERSE) {
+                rc = build_inverse(threads) == 0 ? 0 : -2;
+            } else {
+                print("no inverse or forward map being used\n");
+                rc = -2;
+            }
         }
+        ms_map = ms_since(t0);
     }
     // Whatever was mapped before a failure is still rendered by the reference;
     // publish the (possibly empty) map in every case.
+    t0 = clk::now();
     finish_build();
+    char t[160];
+    snprintf(t, sizeof t, "; script %.1f ms, zoom %.1f ms, map %.1f ms, finish %.1f ms", ms_script, ms_zoom, ms_map, ms_since(t0));
+    build_info_ += t;
     return rc;
 }
 
@@ -1377,41 +1415,86 @@ void FisheyeHost::finish_build() {
     packed_.resize(area);
     span_off_.assign(static_cast<size_t>(height_px_) + 1, 0);
     spans_.clear();
-    int64_t mapped = 0;
     for (int p = 0; p < kMaxPlates; ++p) {
         plate_rect_[p][0] = plate_rect_[p][1] = platesize_;
         plate_rect_[p][2] = plate_rect_[p][3] = -1;
     }
-    const int ps2 = platesize_ * platesize_;
-    for (int y = 0; y < height_px_; ++y) {
-        span_off_[static_cast<size_t>(y)] = static_cast<int32_t>(spans_.size() / 2);
-        int run_start = -1;
-        for (int x = 0; x < width_px_; ++x) {
-            size_t at = static_cast<size_t>(y) * width_px_ + x;
-            int32_t ix = idx_[at];
-            if (ix >= 0) {
-                uint32_t t = tint_[at] == 255 ? 7u : static_cast<uint32_t>(tint_[at] & 7);
-                packed_[at] = 0x80000000u | (t << 28) | static_cast<uint32_t>(ix);
-                ++mapped;
-                int *r = plate_rect_[ix / ps2];
-                const int rem = ix % ps2, ty = rem / platesize_, tx = rem % platesize_;
-                if (tx < r[0]) r[0] = tx;
-                if (ty < r[1]) r[1] = ty;
-                if (tx > r[2]) r[2] = tx;
-                if (ty > r[3]) r[3] = ty;
-                if (run_start < 0) run_start = x;
-            } else {
-                packed_[at] = 7u << 28;
-                if (run_start >= 0) {
-                    spans_.push_back(run_start);
-                    spans_.push_back(x);
-                    run_start = -1;
+    // rows are independent: chunks of rows in parallel, stitched together in order afterwards
+    struct Part {
+        std::vector<int32_t> spans;      // pairs
+        std::vector<int32_t> row_count;  // spans per row
+        int64_t mapped = 0;
+        int rect[kMaxPlates][4];
+    };
+    const int rows_per = 16;
+    const int nchunks = (height_px_ + rows_per - 1) / rows_per;
+    std::vector<Part> parts(static_cast<size_t>(nchunks));
+    const int ps = platesize_;
+    const int ps2 = ps * ps;
+    const bool pow2 = (ps & (ps - 1)) == 0;
+    int shift = 0;
+    while ((1 << shift) < ps) ++shift;
+    parallel_for(nchunks, fallback_threads_, [&](int ch) {
+        Part &pt = parts[static_cast<size_t>(ch)];
+        for (int p = 0; p < kMaxPlates; ++p) {
+            pt.rect[p][0] = pt.rect[p][1] = ps;
+            pt.rect[p][2] = pt.rect[p][3] = -1;
+        }
+        const int y0 = ch * rows_per, y1 = std::min(height_px_, y0 + rows_per);
+        for (int y = y0; y < y1; ++y) {
+            int run_start = -1;
+            const size_t before = pt.spans.size();
+            for (int x = 0; x < width_px_; ++x) {
+                const size_t at = static_cast<size_t>(y) * width_px_ + x;
+                const int32_t ix = idx_[at];
+                if (ix >= 0) {
+                    const uint32_t t = tint_[at] == 255 ? 7u : static_cast<uint32_t>(tint_[at] & 7);
+                    packed_[at] = 0x80000000u | (t << 28) | static_cast<uint32_t>(ix);
+                    ++pt.mapped;
+                    int plate = 0, rem = ix;
+                    while (rem >= ps2) {
+                        rem -= ps2;
+                        ++plate;
+                    }
+                    int *r = pt.rect[plate < kMaxPlates ? plate : kMaxPlates - 1];
+                    const int ty = pow2 ? rem >> shift : rem / ps;
+                    const int tx = rem - ty * ps;
+                    if (tx < r[0]) r[0] = tx;
+                    if (ty < r[1]) r[1] = ty;
+                    if (tx > r[2]) r[2] = tx;
+                    if (ty > r[3]) r[3] = ty;
+                    if (run_start < 0) run_start = x;
+                } else {
+                    packed_[at] = 7u << 28;
+                    if (run_start >= 0) {
+                        pt.spans.push_back(run_start);
+                        pt.spans.push_back(x);
+                        run_start = -1;
+                    }
                 }
             }
+            if (run_start >= 0) {
+                pt.spans.push_back(run_start);
+                pt.spans.push_back(width_px_);
+            }
+            pt.row_count.push_back(static_cast<int32_t>((pt.spans.size() - before) / 2));
         }
-        if (run_start >= 0) {
-            spans_.push_back(run_start);
-            spans_.push_back(width_px_);
+    });
+    int64_t mapped = 0;
+    int row = 0;
+    for (const Part &pt : parts) {
+        int32_t base = static_cast<int32_t>(spans_.size() / 2);
+        for (int32_t n : pt.row_count) {
+            span_off_[static_cast<size_t>(row++)] = base;
+            base += n;
+        }
+        spans_.insert(spans_.end(), pt.spans.begin(), pt.spans.end());
+        mapped += pt.mapped;
+        for (int p = 0; p < kMaxPlates; ++p) {
+            if (pt.rect[p][0] < plate_rect_[p][0]) plate_rect_[p][0] = pt.rect[p][0];
+            if (pt.rect[p][1] < plate_rect_[p][1]) plate_rect_[p][1] = pt.rect[p][1];
+            if (pt.rect[p][2] > plate_rect_[p][2]) plate_rect_[p][2] = pt.rect[p][2];
+            if (pt.rect[p][3] > plate_rect_[p][3]) plate_rect_[p][3] = pt.rect[p][3];
         }
     }
     span_off_[static_cast<size_t>(height_px_)] = static_cast<int32_t>(spans_.size() / 2);

@@ -71,11 +71,13 @@ public:
     // outside the translatable subset, go through the interpreter on `fallback_threads`.
     int build_lensmap(int width, int height, int platesize, int threads);
     using DeviceBuilder = bool (*)(void *user, const std::string &cuda_source, const LensBuildParams &p, uint32_t *cand, std::string *err);
-    void set_device_builder(DeviceBuilder fn, void *user, int fallback_threads) {
+    void set_device_builder(DeviceBuilder fn, void *user) {
         device_builder_ = fn;
         device_builder_user_ = user;
-        fallback_threads_ = fallback_threads < 1 ? 1 : fallback_threads;
     }
+    // host threads for the fallback evaluation and for the per-pixel passes after the map is known
+    void set_worker_threads(int n) { fallback_threads_ = n < 1 ? 1 : n; }
+    int worker_threads() const { return fallback_threads_; }
     // one line about how the last lensmap was built ("device: ..." / "host: ...")
     const std::string &build_info() const { return build_info_; }
     bool needs_rebuild(int width, int height, int platesize) const;

@@ -4,22 +4,18 @@
 #include <cstring>
 
 #include "../../include/blinky_b200.h"
+#include "parallel.h"
 
 namespace blinky {
 
-TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box) {
-    TilePlan plan;
-    plan.width = width;
-    plan.height = height;
-    plan.platesize = platesize;
-    plan.tiles_x = (width + kTileW - 1) / kTileW;
-    plan.tiles_y = (height + kTileH - 1) / kTileH;
-    plan.tiles.reserve(static_cast<size_t>(plan.tiles_x) * plan.tiles_y);
+namespace {
+
+// one row of tiles; entry offsets are relative to the row's own entry buffer
+void plan_tile_row(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int ty, TilePlan &plan) {
     const uint32_t ps = static_cast<uint32_t>(platesize);
     const uint32_t ps2 = ps * ps;
     std::vector<uint32_t> tile(kTilePixels);
-
-    for (int ty = 0; ty < plan.tiles_y; ++ty) {
+    {
         for (int tx = 0; tx < plan.tiles_x; ++tx) {
             const int x0 = tx * kTileW, y0 = ty * kTileH;
             // collect the tile (pixels beyond the frame edge are unmapped)
@@ -108,7 +104,45 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
             plan.tiles.push_back(d);
         }
     }
-    plan.entries.resize((plan.entries.size() + 15) / 16 * 16 + 16);
+}
+
+}  // namespace
+
+TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int threads) {
+    TilePlan plan;
+    plan.width = width;
+    plan.height = height;
+    plan.platesize = platesize;
+    plan.tiles_x = (width + kTileW - 1) / kTileW;
+    plan.tiles_y = (height + kTileH - 1) / kTileH;
+    std::vector<TilePlan> rows(static_cast<size_t>(plan.tiles_y));
+    parallel_for(plan.tiles_y, threads, [&](int ty) {
+        TilePlan &r = rows[static_cast<size_t>(ty)];
+        r.tiles_x = plan.tiles_x;
+        r.tiles.reserve(static_cast<size_t>(plan.tiles_x));
+        plan_tile_row(packed, width, height, platesize, allow_box, ty, r);
+    });
+    // stitch the rows together in order (every entry block is a multiple of 16 bytes)
+    size_t total = 0;
+    for (const TilePlan &r : rows) total += r.entries.size();
+    plan.entries.resize(total + 16);
+    plan.tiles.reserve(static_cast<size_t>(plan.tiles_x) * plan.tiles_y);
+    size_t base = 0;
+    for (const TilePlan &r : rows) {
+        if (!r.entries.empty()) memcpy(plan.entries.data() + base, r.entries.data(), r.entries.size());
+        for (TileDesc d : r.tiles) {
+            if (d.type != TILE_EMPTY) d.entry_offset += static_cast<uint32_t>(base);
+            plan.tiles.push_back(d);
+        }
+        base += r.entries.size();
+        plan.n_empty += r.n_empty;
+        plan.n_box += r.n_box;
+        plan.n_box_full += r.n_box_full;
+        plan.n_gather += r.n_gather;
+        plan.box_bytes += r.box_bytes;
+        for (uint16_t shape : r.shapes)
+            if (std::find(plan.shapes.begin(), plan.shapes.end(), shape) == plan.shapes.end()) plan.shapes.push_back(shape);
+    }
     // BOX tiles first: the TMA ring kernel walks [0, n_box), the gather kernel the rest
     std::stable_partition(plan.tiles.begin(), plan.tiles.end(),
                           [](const TileDesc &d) { return d.type == TILE_BOX || d.type == TILE_BOX_FULL; });

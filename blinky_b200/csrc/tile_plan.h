@@ -61,6 +61,7 @@ struct TilePlan {
 // packed: [height][width] entries in the BLINKY_LM_* format.  allow_box = false
 // forces every non-empty tile to GATHER (e.g. platesize not a multiple of 16,
 // which TMA cannot address).
-TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box);
+// Tile rows are classified on `threads` host threads; the result does not depend on the thread count.
+TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int threads = 1);
 
 }  // namespace blinky

@@ -15,8 +15,9 @@
  * the reference adds -llua (engine/Makefile:834-841).  See INTEGRATION.md.
  *
  * Differences a maintainer should know about:
- *  - the lensmap is built in one shot (optionally on several host threads)
- *    instead of being time-sliced over frames (fisheye.c:301-322, 819-826);
+ *  - the lensmap is built in one shot — lens_inverse translated to CUDA and evaluated on
+ *    the GPU, or interpreted on host threads — instead of being time-sliced over frames
+ *    (fisheye.c:301-322, 819-826);
  *  - globe.pixels lives in pinned host memory so plates upload with
  *    cudaMemcpyAsync; only plates the lens looks at are uploaded;
  *  - f_saveglobe writes the PCX files itself (into com_gamedir) instead of going
@@ -50,7 +51,7 @@ double fisheye_plate_fov;
 static blinky_ctx *b200;
 static byte *globe_pixels;      /* pinned; [numplates][platesize][platesize] like GLOBEPIXEL (fisheye.c:349) */
 static size_t globe_bytes;
-static int build_threads = 1;
+static int build_threads = 0; /* 0 = lens evaluated on the GPU (BLINKY_BUILD_THREADS overrides) */
 
 /* exposed for harnesses/tests (not part of the engine seam) */
 blinky_ctx *F_B200_Context(void) { return b200; }

@@ -244,6 +244,9 @@ int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_st
 /* one-line description of how the current lensmap was tiled for the TMA kernel
  * (tile counts per class, staged bytes per pixel); "" before a build */
 const char *blinky_plan_summary(blinky_ctx *ctx);
+/* FNV-1a digest of the tile table + entry blocks planned on `threads` host threads (the plan
+ * must not depend on the thread count; used by the tests) */
+uint64_t blinky_plan_digest(blinky_ctx *ctx, int threads);
 /* number of kernel launches issued by this context so far */
 int64_t blinky_launch_count(blinky_ctx *ctx);
 /* last warp kernel's name and launch geometry, for reports */

@@ -345,3 +345,17 @@ def test_saveglobe_pcx_matches_compiled_reference(bb, host, ref, tmp_path):
     host.clear_log()
     host.command("f_saveglobe")
     assert "f_saveglobe <name> [full flag=0]" in host.log
+
+
+def test_tile_plan_and_lensmap_do_not_depend_on_the_thread_count(host):
+    """the per-pixel host passes (lensmap finish, tile planning) are split over threads"""
+    for globe, lens, size in [("cube", "panini", (333, 201, 96)), ("tetra", "quincuncial", (160, 97, 64)), ("cube", "hammer", (256, 128, 80))]:
+        host.command(f"f_globe {globe}")
+        host.command(f"f_lens {lens}")
+        host.build_lensmap(*size, threads=1)
+        packed = host.lensmap_packed().copy()
+        d1 = host.plan_digest(1)
+        assert d1 != 0 and d1 == host.plan_digest(3) == host.plan_digest(16)
+        host.build_lensmap(*size, threads=5)
+        assert np.array_equal(packed, host.lensmap_packed())
+        assert d1 == host.plan_digest(7)
