@@ -60,7 +60,7 @@ _SIGNATURES = [
     ("blinky_needs_rebuild", c_int, [_CTX, c_int, c_int, c_int]),
     ("blinky_build_info", c_char_p, [_CTX]),
     ("blinky_plan_digest", ctypes.c_uint64, [_CTX, c_int]),
-    ("blinky_compile_lens", c_int, [_CTX, POINTER(c_size_t)]),
+    ("blinky_compile_lens", c_int, [_CTX, c_int, POINTER(c_size_t)]),
     ("blinky_fisheye_enabled", c_int, [_CTX]),
     ("blinky_lens_valid", c_int, [_CTX]),
     ("blinky_globe_valid", c_int, [_CTX]),
@@ -246,10 +246,10 @@ class Fisheye:
     def plan_digest(self, threads: int = 1) -> int:
         return int(self._lib.blinky_plan_digest(self._ctx, threads))
 
-    def compile_lens(self) -> int:
+    def compile_lens(self, forward: bool = False) -> int:
         """Translate the current lens to CUDA and compile it with NVRTC; returns the cubin size."""
         n = c_size_t()
-        self._check(self._lib.blinky_compile_lens(self._ctx, ctypes.byref(n)))
+        self._check(self._lib.blinky_compile_lens(self._ctx, int(forward), ctypes.byref(n)))
         return n.value
 
     def needs_rebuild(self, width: int, height: int, platesize: int = 0) -> bool:
@@ -329,13 +329,14 @@ class Fisheye:
         st = self._lib.blinky_lens_forward(self._ctx, rx, ry, rz, ctypes.byref(x), ctypes.byref(y))
         return st, (x.value, y.value)
 
-    def lens_source(self, cuda: bool = False) -> str:
-        """The current ``lens_inverse`` translated to C++/CUDA (raises when not translatable)."""
-        n = self._lib.blinky_lens_source(self._ctx, int(cuda), None, 0)
+    def lens_source(self, cuda: bool = False, forward: bool = False) -> str:
+        """The current ``lens_inverse`` (or ``lens_forward``) translated to C++/CUDA (raises when not translatable)."""
+        flavour = int(cuda) | (2 if forward else 0)
+        n = self._lib.blinky_lens_source(self._ctx, flavour, None, 0)
         if n < 0:
             self._check(n)
         buf = ctypes.create_string_buffer(n + 1)
-        self._lib.blinky_lens_source(self._ctx, int(cuda), ctypes.addressof(buf), n + 1)
+        self._lib.blinky_lens_source(self._ctx, flavour, ctypes.addressof(buf), n + 1)
         return buf.value.decode()
 
     def write_config(self) -> str:

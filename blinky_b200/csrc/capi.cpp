@@ -60,11 +60,6 @@ int usable_cpus() {
     return n < 1 ? 1 : n;
 }
 
-bool device_lens_builder(void *user, const std::string &src, const LensBuildParams &p, uint32_t *cand, std::string *err) {
-    blinky_ctx *c = static_cast<blinky_ctx *>(user);
-    return c->lens_dev->build(src, p, cand, err);
-}
-
 bool upload(blinky_ctx *c) {
     if (!c->dev || !c->host.built()) return true;
     blinky::LensmapUpload lm;
@@ -112,7 +107,7 @@ int blinky_create(int device, blinky_ctx **out) {
         try {
             c->dev.reset(new WarpDevice(device));
             c->lens_dev.reset(new LensDevice(device));
-            c->host.set_device_builder(device_lens_builder, c);
+            c->host.set_device_builder(c->lens_dev.get());
         } catch (std::exception &e) {
             // no silent CPU fallback: hand back a context that explains itself
             c->err = e.what();
@@ -193,7 +188,7 @@ int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, 
     if (threads < 0) threads = usable_cpus();
     int rc = ctx->host.build_lensmap(width, height, platesize, threads);
     ctx->build_info = ctx->host.build_info();
-    if (ctx->lens_dev && ctx->build_info.compare(0, 7, "device:") == 0) {
+    if (ctx->lens_dev && ctx->build_info.compare(0, 6, "device") == 0) {
         char t[96];
         snprintf(t, sizeof t, " (NVRTC %.0f ms, kernel %.3f ms)", ctx->lens_dev->last_compile_ms(), ctx->lens_dev->last_kernel_ms());
         ctx->build_info += t;
@@ -218,12 +213,12 @@ int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, 
 
 const char *blinky_build_info(blinky_ctx *ctx) { return ctx->build_info.c_str(); }
 
-int blinky_compile_lens(blinky_ctx *ctx, size_t *cubin_bytes) {
+int blinky_compile_lens(blinky_ctx *ctx, int forward, size_t *cubin_bytes) {
     std::string src, why;
-    if (!ctx->host.lens_device_source(true, &src, &why)) return set_err(ctx, BLINKY_E_SCRIPT, why);
+    if (!ctx->host.lens_device_source(true, &src, &why, forward != 0)) return set_err(ctx, BLINKY_E_SCRIPT, why);
     std::vector<char> cubin;
     std::string log;
-    if (!LensDevice::compile(src, &cubin, &log)) return set_err(ctx, BLINKY_E_CUDA, log);
+    if (!LensDevice::compile(src, forward != 0, &cubin, &log)) return set_err(ctx, BLINKY_E_CUDA, log);
     if (cubin_bytes) *cubin_bytes = cubin.size();
     return BLINKY_OK;
 }
@@ -299,9 +294,9 @@ int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double
     return ctx->host.lens_forward(rx, ry, rz, x, y);
 }
 
-int blinky_lens_source(blinky_ctx *ctx, int cuda, char *buf, size_t bufsize) {
+int blinky_lens_source(blinky_ctx *ctx, int flavour, char *buf, size_t bufsize) {
     std::string s, why;
-    if (!ctx->host.lens_device_source(cuda != 0, &s, &why)) return set_err(ctx, BLINKY_E_SCRIPT, why);
+    if (!ctx->host.lens_device_source((flavour & 1) != 0, &s, &why, (flavour & 2) != 0)) return set_err(ctx, BLINKY_E_SCRIPT, why);
     if (buf && bufsize) {
         size_t n = s.size() < bufsize - 1 ? s.size() : bufsize - 1;
         memcpy(buf, s.data(), n);

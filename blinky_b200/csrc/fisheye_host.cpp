@@ -9,6 +9,7 @@
 #include "lua_transpile.h"
 #include "parallel.h"
 
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <chrono>
@@ -831,16 +832,17 @@ int FisheyeHost::call_forward(Worker &w, const float ray[3], double *x, double *
     return -1;
 }
 
-bool FisheyeHost::lens_device_source(bool cuda, std::string *source, std::string *why) {
-    if (!fn_inverse_.is_function()) {
-        *why = "the lens has no lens_inverse";
+bool FisheyeHost::lens_device_source(bool cuda, std::string *source, std::string *why, bool forward) {
+    const Value &fn = forward ? fn_forward_ : fn_inverse_;
+    if (!fn.is_function()) {
+        *why = forward ? "the lens has no lens_forward" : "the lens has no lens_inverse";
         return false;
     }
     if (fn_globe_plate_.is_function()) {
         *why = "the globe selects plates with a script function (globe_plate)";
         return false;
     }
-    TranspileResult r = transpile_lens(*lua_, fn_inverse_);
+    TranspileResult r = forward ? transpile_lens_forward(*lua_, fn) : transpile_lens(*lua_, fn);
     if (!r.ok) {
         *why = r.error;
         return false;
@@ -1113,9 +1115,7 @@ int FisheyeHost::run_inverse_workers(int threads, int nitems, int *display, F it
     return rc;
 }
 
-int FisheyeHost::build_inverse_device(int *display, std::string *why) {
-    std::string src;
-    if (!lens_device_source(true, &src, why)) return 1;
+LensBuildParams FisheyeHost::device_params() const {
     LensBuildParams p;
     memset(&p, 0, sizeof p);
     p.width = width_px_;
@@ -1138,9 +1138,16 @@ int FisheyeHost::build_inverse_device(int *display, std::string *why) {
         }
         p.plates[i].dist = pl.dist;
     }
+    return p;
+}
+
+int FisheyeHost::build_inverse_device(int *display, std::string *why) {
+    std::string src;
+    if (!lens_device_source(true, &src, why)) return 1;
+    const LensBuildParams p = device_params();
     const size_t area = idx_.size();
     std::vector<uint32_t> cand(area);
-    if (!device_builder_(device_builder_user_, src, p, cand.data(), why)) return 1;
+    if (!device_builder_->build(src, p, cand.data(), why)) return 1;
 
     std::vector<int32_t> undecided;
     {
@@ -1278,10 +1285,67 @@ void FisheyeHost::draw_quad(const int *tl, const int *tr, const int *bl, const i
     }
 }
 
-int FisheyeHost::build_forward(int /*threads*/) {
+// Forward lenses on the GPU: lens_forward is evaluated at every plate grid point by the translated
+// kernel, the interpreter settles the points the device could not decide, then the quads are
+// rasterised on the device in the reference's writer order (lens_device.cu).
+int FisheyeHost::build_forward_device(std::string *why) {
+    std::string src;
+    if (!lens_device_source(true, &src, why, true)) return 1;
+    const LensBuildParams p = device_params();
+    std::vector<uint32_t> undecided;
+    if (!device_builder_->forward_points(src, p, &undecided, why)) return 1;
+    std::vector<ForwardPatch> patches(undecided.size());
+    const int n1 = platesize_ + 1;
+    const int chunk = 256;
+    const int nitems = static_cast<int>((undecided.size() + chunk - 1) / chunk);
+    int display_unused[kMaxPlates] = {0, 0, 0, 0, 0, 0};
+    std::atomic<int> bad(0);
+    // the workers only need lens_forward; the generic worker setup parks lens_inverse (may be nil: fine)
+    lua_->set_global("__blinky_forward", fn_forward_);
+    int rc = run_inverse_workers(undecided.size() >= 4096 ? fallback_threads_ : 1, nitems, display_unused, [&](Worker &w, int item, int *) {
+        if (!w.forward.is_function()) w.forward = w.L->get_global("__blinky_forward");
+        const size_t b = static_cast<size_t>(item) * chunk, e = std::min(undecided.size(), b + chunk);
+        for (size_t k = b; k < e; ++k) {
+            const uint32_t pt = undecided[k];
+            const int i = static_cast<int>(pt % n1), j = static_cast<int>(pt / n1 % n1), plate = static_cast<int>(pt / n1 / n1);
+            ForwardPatch &out = patches[k];
+            out.point = pt;
+            out.lx = out.ly = 0;
+            out.status = uv_to_screen(w, plate, (i - 0.5) / platesize_, (j - 0.5) / platesize_, &out.lx, &out.ly);
+            if (out.status < 0) bad.store(1);
+        }
+        w.forward = Value();
+        return 0;
+    });
+    lua_->set_global("__blinky_forward", Value());
+    if (rc != 0 || bad.load()) return -1;
+    int display[kMaxPlates] = {0, 0, 0, 0, 0, 0};
+    std::vector<std::pair<uint32_t, int>> messages;
+    if (!device_builder_->forward_finish(patches, idx_.data(), tint_.data(), display, &messages, why)) {
+        std::fill(idx_.begin(), idx_.end(), -1);
+        std::fill(tint_.begin(), tint_.end(), 255);
+        return 1;
+    }
+    std::sort(messages.begin(), messages.end());
+    for (auto &m : messages) print("%d > maxdiff\n", m.second);
+    for (int i = 0; i < kMaxPlates; ++i) plates_[i].display = display[i];
+    char info[160];
+    snprintf(info, sizeof info, "device (forward): %zu of %zu grid points re-evaluated by the interpreter", undecided.size(),
+             static_cast<size_t>(numplates_) * n1 * n1);
+    build_info_ = info;
+    return 0;
+}
+
+int FisheyeHost::build_forward(int threads) {
     if (!fn_forward_.is_function()) {
         print("lens_forward is not a function\n");
         return -2;
+    }
+    if (threads == 0) {
+        std::string why = "no GPU lens builder installed";
+        int rc = device_builder_ ? build_forward_device(&why) : 1;
+        if (rc != 1) return rc;
+        build_info_ = "host (forward lens; " + why + ")";
     }
     Worker w;
     w.L = lua_.get();

@@ -70,11 +70,7 @@ public:
     // lens translates (lua_transpile.h); pixels the device cannot decide exactly, and lenses
     // outside the translatable subset, go through the interpreter on `fallback_threads`.
     int build_lensmap(int width, int height, int platesize, int threads);
-    using DeviceBuilder = bool (*)(void *user, const std::string &cuda_source, const LensBuildParams &p, uint32_t *cand, std::string *err);
-    void set_device_builder(DeviceBuilder fn, void *user) {
-        device_builder_ = fn;
-        device_builder_user_ = user;
-    }
+    void set_device_builder(DeviceLensBuilder *b) { device_builder_ = b; }
     // host threads for the fallback evaluation and for the per-pixel passes after the map is known
     void set_worker_threads(int n) { fallback_threads_ = n < 1 ? 1 : n; }
     int worker_threads() const { return fallback_threads_; }
@@ -136,7 +132,7 @@ public:
 
     // C++/CUDA source of the current lens_inverse (lua_transpile.h); false + reason when the
     // lens is outside the transpilable subset
-    bool lens_device_source(bool cuda, std::string *source, std::string *why);
+    bool lens_device_source(bool cuda, std::string *source, std::string *why, bool forward = false);
 
     // pure converters, exposed for the Lua-visible wrappers
     static void latlon_to_ray(double lat, double lon, float ray[3]);
@@ -167,6 +163,8 @@ private:
     int run_inverse_workers(int threads, int nitems, int *display, F item);
     int build_inverse(int threads);
     int build_inverse_device(int *display, std::string *why);  // 0 ok, -1 script failure, 1 = not possible (why)
+    int build_forward_device(std::string *why);                // same convention
+    LensBuildParams device_params() const;
     int build_forward(int threads);
     int uv_to_screen(Worker &w, int plate, double u, double v, int *lx, int *ly);
     void draw_quad(const int *tl, const int *tr, const int *bl, const int *br, int plate, int px, int py, int *display);
@@ -181,8 +179,7 @@ private:
     std::unique_ptr<minilua::State> lua_;
     minilua::Value fn_inverse_, fn_forward_, fn_globe_plate_;  // registry refs, :328-332
 
-    DeviceBuilder device_builder_ = nullptr;
-    void *device_builder_user_ = nullptr;
+    DeviceLensBuilder *device_builder_ = nullptr;  // not owned
     int fallback_threads_ = 1;
     std::string build_info_;
 

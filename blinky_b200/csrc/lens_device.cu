@@ -81,6 +81,64 @@ extern "C" __global__ void __launch_bounds__(128) lt_build(const __grid_constant
 }
 )KRN";
 
+// Forward builder, step 1 (fisheye.c:2227-2243 uv_to_screen over the grid of fisheye.c:2151-2189):
+// grid point (plate, j, i) sits at u = (i - 0.5)/ps, v = (j - 0.5)/ps.
+const char *kForwardKernelSource = R"KRN(
+struct LtParams {
+    int width, height, platesize, numplates;
+    double scale;
+    double rubix_block, rubix_pad, rubix_unit_px;
+    double uv_dist[6];
+    LtPlate plates[6];
+};
+
+// (int) of a double with an error bound: undecided when an integer lies within the bound, or when the
+// value is outside int range / NaN (x86 and CUDA convert those differently)
+static __device__ __forceinline__ int lt_trunc_int(Ctx &c, LtD x) {
+    if (!(fabs(x.v) < 2147483000.0)) { c.flag |= LT_RISK_NEAR; return 0; }
+    if (!(x.e == 0.0)) {
+        const double n = rint(x.v);
+        if (!(fabs(x.v - n) > 2.0 * x.e)) c.flag |= LT_RISK_NEAR;
+    }
+    return (int)x.v;
+}
+
+extern "C" __global__ void __launch_bounds__(128) lt_forward_points(const __grid_constant__ LtParams P, int2 *__restrict__ grid,
+                                                                    unsigned char *__restrict__ status, unsigned *__restrict__ undecided,
+                                                                    unsigned *__restrict__ counters, unsigned undecided_cap) {
+    const int n1 = P.platesize + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, plate = blockIdx.z;
+    if (i >= n1) return;
+    const unsigned point = ((unsigned)plate * n1 + j) * n1 + i;
+    Ctx c;
+    c.flag = 0;
+    c.steps = 0;
+    c.plates = P.plates;
+    c.numplates = P.numplates;
+    lt_init_mut(c);
+    // plate_uv_to_ray (fisheye.c:1198-1214) for exact u, v
+    double ray[3];
+    lt_plate_to_ray(c, LtD((double)plate), LtD((i - 0.5) / P.platesize), LtD((j - 0.5) / P.platesize), ray);
+    LtD r[2];
+    int2 out = make_int2(0, 0);
+    unsigned char st = 0;
+    if (lt_entry(c, ray[0], ray[1], ray[2], r)) {
+        st = 1;
+        out.x = lt_trunc_int(c, r[0] / LtD(P.scale) + LtD((double)(P.width / 2)));
+        out.y = lt_trunc_int(c, -r[1] / LtD(P.scale) + LtD((double)(P.height / 2)));
+    } else {
+        atomicAdd(&counters[1], 1u);   // a nil: the stale-value pass is needed
+    }
+    if (c.flag) {
+        st = 2;
+        const unsigned at = atomicAdd(&counters[0], 1u);
+        if (at < undecided_cap) undecided[at] = point;
+    }
+    grid[point] = out;
+    status[point] = st;
+}
+)KRN";
+
 struct Nvrtc {
     void *lib = nullptr;
     decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
@@ -154,20 +212,214 @@ struct LensDevice::Module {
     CUfunction fn = nullptr;
 };
 
+// device buffers that live between forward_points() and forward_finish()
+struct LensDevice::ForwardState {
+    LensBuildParams p;
+    size_t npoints = 0;
+    int2 *grid = nullptr;
+    unsigned char *status = nullptr;
+    unsigned *undecided = nullptr;
+    unsigned *counters = nullptr;  // [0] undecided points, [1] nil results, [2] messages, [3..8] display flags
+    unsigned nil_count = 0;
+};
+
+namespace {
+
+constexpr unsigned kUndecidedCap = 1u << 20;
+constexpr unsigned kMessageCap = 4096;
+
+// ---- forward builder, steps 2-4 (static kernels; this file is compiled with --fmad=false) ----------
+
+struct FwdGeom {
+    int width, height, ps, numplates;
+    double rubix_block, rubix_pad, rubix_unit_px;
+    LensBuildParams::PlateF plates[6];
+};
+
+__global__ void fwd_patch_kernel(int2 *grid, unsigned char *status, const ForwardPatch *patches, unsigned n) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const ForwardPatch pt = patches[k];
+    status[pt.point] = static_cast<unsigned char>(pt.status);
+    if (pt.status == 1) grid[pt.point] = make_int2(pt.lx, pt.ly);
+}
+
+// The reference keeps two row buffers and `continue`s over nil results (fisheye.c:2151-2189), so a
+// nil slot shows whatever the buffer held before: the row two steps earlier, the previous plate's last
+// rows at a plate start, zero at the very beginning.  One thread per (column, buffer) replays its chain.
+__global__ void fwd_stale_kernel(int2 *grid, const unsigned char *status, int ps, int numplates) {
+    const int n1 = ps + 1;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n1) return;
+    const int i = t >> 1;
+    int j = (t & 1) ? ps - 1 : ps;  // buffer `bot` starts with row ps, buffer `top` with row ps-1
+    int2 last = make_int2(0, 0);
+    for (int p = 0; p < numplates;) {
+        const size_t row = (static_cast<size_t>(p) * n1 + j) * n1;
+        // slot 1 is skipped together with slot 0 (the `continue` in the px == 0 branch)
+        const bool valid = status[row + i] == 1 && !(i == 1 && status[row] != 1);
+        if (valid) last = grid[row + i];
+        else grid[row + i] = last;
+        if (j >= 2) {
+            j -= 2;
+        } else {
+            j = j == 1 ? ps : ps - 1;  // the buffer that ended as `bot` (row 1) takes row ps of the next plate
+            ++p;
+        }
+    }
+}
+
+__device__ __forceinline__ float fdot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+struct FwdOut {
+    unsigned *idxkey, *tintkey, *counters;
+    uint2 *messages;
+};
+
+__device__ __forceinline__ void fwd_set(const FwdGeom &g, const FwdOut &o, int lx, int ly, unsigned key, bool ongrid, int plate) {
+    if (lx < 0 || lx >= g.width || ly < 0 || ly >= g.height) return;  // set_lensmap_from_plate's screen check
+    o.counters[3 + plate] = 1u;                                         // display flag (benign race: all writers store 1)
+    const size_t at = static_cast<size_t>(lx) + static_cast<size_t>(ly) * g.width;
+    atomicMax(&o.idxkey[at], key);
+    if (!ongrid) atomicMax(&o.tintkey[at], key);
+}
+
+// draw_quad (fisheye.c:2246-2338) for the texel (plate, px, py); key orders the writers like the
+// reference's loops do (plate ascending, py descending, px ascending): the highest key wins.
+__global__ void __launch_bounds__(128) fwd_raster_kernel(const __grid_constant__ FwdGeom g, const int2 *__restrict__ grid, FwdOut o) {
+    const int ps = g.ps, n1 = ps + 1;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, plate = blockIdx.z;
+    if (px >= ps) return;
+    // the texel belongs to this plate only if the plate wins the ray's argmax (:2193-2199)
+    {
+        const LensBuildParams::PlateF &P = g.plates[plate];
+        double u = static_cast<double>(px) / ps, v = static_cast<double>(py) / ps;
+        u -= 0.5;
+        v -= 0.5;
+        v = -v;
+        float r[3] = {0.0f, 0.0f, 0.0f};
+        const float fu = static_cast<float>(u), fv = static_cast<float>(v);
+        for (int k = 0; k < 3; ++k) r[k] = r[k] + P.dist * P.forward[k];
+        for (int k = 0; k < 3; ++k) r[k] = r[k] + fu * P.right[k];
+        for (int k = 0; k < 3; ++k) r[k] = r[k] + fv * P.up[k];
+        float len = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        len = static_cast<float>(sqrt(static_cast<double>(len)));
+        if (len) {
+            const float inv = 1 / len;
+            r[0] *= inv;
+            r[1] *= inv;
+            r[2] *= inv;
+        }
+        int best = 0;
+        double best_dp = -2;
+        for (int k = 0; k < g.numplates; ++k) {
+            const double dp = static_cast<double>(fdot3(r, g.plates[k].forward));
+            if (dp > best_dp) {
+                best_dp = dp;
+                best = k;
+            }
+        }
+        if (best != plate) return;
+    }
+    const unsigned key = (static_cast<unsigned>(plate) * ps + (ps - 1 - py)) * ps + px + 1u;
+    const double ux = static_cast<double>(px) / g.rubix_unit_px, uy = static_cast<double>(py) / g.rubix_unit_px;
+    const bool ongrid = fmod(ux, g.rubix_block) < g.rubix_pad || fmod(uy, g.rubix_block) < g.rubix_pad;
+
+    const size_t top = (static_cast<size_t>(plate) * n1 + py) * n1, bot = top + n1;
+    const int2 c0 = grid[top + px], c1 = grid[top + px + 1], c2 = grid[bot + px + 1], c3 = grid[bot + px];  // tl, tr, br, bl: clockwise
+    const int cx[4] = {c0.x, c1.x, c2.x, c3.x}, cy[4] = {c0.y, c1.y, c2.y, c3.y};
+    int x = cx[0], y = cy[0];
+    int minx = x, maxx = x, miny = y, maxy = y;
+    for (int i = 1; i < 4; ++i) {
+        if (cx[i] < minx) minx = cx[i]; else if (cx[i] > maxx) maxx = cx[i];
+        if (cy[i] < miny) miny = cy[i]; else if (cy[i] > maxy) maxy = cy[i];
+    }
+    const int maxdiff = 20;
+    // abs() of an int difference, computed like the host does (wraps the same way on overflow)
+    const int ddx = minx - maxx, ddy = miny - maxy;
+    if ((ddx < 0 ? -ddx : ddx) > maxdiff || (ddy < 0 ? -ddy : ddy) > maxdiff) return;
+    if (miny == maxy && minx == maxx) {
+        fwd_set(g, o, x, y, key, ongrid, plate);
+        return;
+    }
+    if (miny == maxy) {
+        for (int tx = minx; tx <= maxx; ++tx) fwd_set(g, o, tx, miny, key, ongrid, plate);
+        return;
+    }
+    if (minx == maxx) {
+        for (int ty = miny; ty <= maxy; ++ty) fwd_set(g, o, x, ty, key, ongrid, plate);
+        return;
+    }
+    for (y = miny; y <= maxy; ++y) {
+        int tx[2] = {minx, maxx};
+        int found = 0;
+        int j = 3;
+        for (int i = 0; i < 4; ++i) {
+            const int ix = cx[i], iy = cy[i], jx = cx[j], jy = cy[j];
+            if ((iy < y && y <= jy) || (jy < y && y <= iy)) {
+                const double dy = jy - iy;
+                const double dx = jx - ix;
+                tx[found] = static_cast<int>(ix + (y - iy) / dy * dx);
+                if (++found == 2) break;
+            }
+            j = i;
+        }
+        if (tx[0] > tx[1]) {
+            const int t = tx[0];
+            tx[0] = tx[1];
+            tx[1] = t;
+        }
+        if (tx[1] - tx[0] > maxdiff) {
+            const unsigned at = atomicAdd(&o.counters[2], 1u);
+            if (at < kMessageCap) o.messages[at] = make_uint2(key, static_cast<unsigned>(tx[1] - tx[0]));
+            return;
+        }
+        for (x = tx[0]; x <= tx[1]; ++x) fwd_set(g, o, x, y, key, ongrid, plate);
+    }
+}
+
+__global__ void fwd_resolve_kernel(const unsigned *__restrict__ idxkey, const unsigned *__restrict__ tintkey, int32_t *__restrict__ idx,
+                                   uint8_t *__restrict__ tint, size_t npix, int ps) {
+    const size_t at = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (at >= npix) return;
+    const unsigned k = idxkey[at];
+    if (k) {
+        const unsigned key = k - 1, px = key % ps, t = key / ps, py = ps - 1 - t % ps, plate = t / ps;
+        idx[at] = static_cast<int32_t>(plate * ps * ps + py * ps + px);
+    } else {
+        idx[at] = -1;
+    }
+    const unsigned tk = tintkey[at];
+    tint[at] = tk ? static_cast<uint8_t>((tk - 1) / ps / ps) : 255;
+}
+
+}  // namespace
+
 LensDevice::~LensDevice() {
+    drop_forward_state();
     for (auto &kv : cache_) {
         if (kv.second->mod && driver().ok) driver().ModuleUnload(kv.second->mod);
         delete kv.second;
     }
 }
 
-bool LensDevice::compile(const std::string &lens_source, std::vector<char> *cubin, std::string *log) {
+void LensDevice::drop_forward_state() {
+    if (!fwd_) return;
+    cudaFree(fwd_->grid);
+    cudaFree(fwd_->status);
+    cudaFree(fwd_->undecided);
+    cudaFree(fwd_->counters);
+    delete fwd_;
+    fwd_ = nullptr;
+}
+
+bool LensDevice::compile(const std::string &lens_source, bool forward, std::vector<char> *cubin, std::string *log) {
     Nvrtc &n = nvrtc();
     if (!n.why.empty()) {
         *log = n.why;
         return false;
     }
-    const std::string src = lens_source + kKernelSource;
+    const std::string src = lens_source + (forward ? kForwardKernelSource : kKernelSource);
     nvrtcProgram prog;
     nvrtcResult rc = n.CreateProgram(&prog, src.c_str(), "lens.cu", 0, nullptr, nullptr);
     if (rc != NVRTC_SUCCESS) {
@@ -196,50 +448,54 @@ bool LensDevice::compile(const std::string &lens_source, std::vector<char> *cubi
     return sz > 0;
 }
 
-bool LensDevice::build(const std::string &lens_source, const LensBuildParams &p, uint32_t *cand, std::string *err) {
-    compile_ms_ = kernel_ms_ = 0;
+LensDevice::Module *LensDevice::module_for(const std::string &lens_source, bool forward, std::string *err) {
+    compile_ms_ = 0;
     if (cudaSetDevice(device_) != cudaSuccess) {
         *err = "cudaSetDevice failed";
-        return false;
+        return nullptr;
     }
     Driver &d = driver();
     if (!d.ok) {
         *err = "CUDA driver entry points unavailable";
-        return false;
+        return nullptr;
     }
-    Module *m = nullptr;
-    auto it = cache_.find(lens_source);
-    if (it != cache_.end()) {
-        m = it->second;
-    } else {
-        auto t0 = std::chrono::steady_clock::now();
-        std::vector<char> cubin;
-        std::string log;
-        if (!compile(lens_source, &cubin, &log)) {
-            *err = log;
-            return false;
-        }
-        cudaFree(nullptr);  // make sure the primary context is current
-        m = new Module;
-        CUresult cr = d.ModuleLoadData(&m->mod, cubin.data());
-        if (cr == CUDA_SUCCESS) cr = d.ModuleGetFunction(&m->fn, m->mod, "lt_build");
-        if (cr != CUDA_SUCCESS) {
-            if (m->mod) d.ModuleUnload(m->mod);
-            delete m;
-            *err = "loading the compiled lens failed (CUresult " + std::to_string(static_cast<int>(cr)) + ")";
-            return false;
-        }
-        if (cache_.size() >= 16) {  // lenses are few; keep the cache from growing without bound
-            for (auto &kv : cache_) {
-                d.ModuleUnload(kv.second->mod);
-                delete kv.second;
-            }
-            cache_.clear();
-        }
-        cache_[lens_source] = m;
-        compile_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const std::string cache_key = (forward ? "F" : "I") + lens_source;
+    auto it = cache_.find(cache_key);
+    if (it != cache_.end()) return it->second;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile(lens_source, forward, &cubin, &log)) {
+        *err = log;
+        return nullptr;
     }
+    cudaFree(nullptr);  // make sure the primary context is current
+    Module *m = new Module;
+    CUresult cr = d.ModuleLoadData(&m->mod, cubin.data());
+    if (cr == CUDA_SUCCESS) cr = d.ModuleGetFunction(&m->fn, m->mod, forward ? "lt_forward_points" : "lt_build");
+    if (cr != CUDA_SUCCESS) {
+        if (m->mod) d.ModuleUnload(m->mod);
+        delete m;
+        *err = "loading the compiled lens failed (CUresult " + std::to_string(static_cast<int>(cr)) + ")";
+        return nullptr;
+    }
+    if (cache_.size() >= 16) {  // lenses are few; keep the cache from growing without bound
+        for (auto &kv : cache_) {
+            d.ModuleUnload(kv.second->mod);
+            delete kv.second;
+        }
+        cache_.clear();
+    }
+    cache_[cache_key] = m;
+    compile_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return m;
+}
 
+bool LensDevice::build(const std::string &lens_source, const LensBuildParams &p, uint32_t *cand, std::string *err) {
+    kernel_ms_ = 0;
+    Module *m = module_for(lens_source, false, err);
+    if (!m) return false;
+    Driver &d = driver();
     const size_t npix = static_cast<size_t>(p.width) * p.height;
     uint32_t *d_cand = nullptr;
     cudaError_t ce = cudaMalloc(&d_cand, npix * sizeof(uint32_t));
@@ -273,6 +529,157 @@ bool LensDevice::build(const std::string &lens_source, const LensBuildParams &p,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d_cand);
+    return ok;
+}
+
+bool LensDevice::forward_points(const std::string &lens_source, const LensBuildParams &p, std::vector<uint32_t> *undecided, std::string *err) {
+    kernel_ms_ = 0;
+    drop_forward_state();
+    Module *m = module_for(lens_source, true, err);
+    if (!m) return false;
+    Driver &d = driver();
+    const size_t n1 = static_cast<size_t>(p.platesize) + 1;
+    const size_t npoints = static_cast<size_t>(p.numplates) * n1 * n1;
+    if (npoints >= 0xFFFFFFFFull) {
+        *err = "too many grid points";
+        return false;
+    }
+    fwd_ = new ForwardState;
+    fwd_->p = p;
+    fwd_->npoints = npoints;
+    cudaError_t ce = cudaMalloc(&fwd_->grid, npoints * sizeof(int2));
+    if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->status, npoints);
+    if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->undecided, kUndecidedCap * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->counters, 16 * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMemset(fwd_->counters, 0, 16 * sizeof(unsigned));
+    if (ce != cudaSuccess) {
+        *err = std::string("cudaMalloc: ") + cudaGetErrorString(ce);
+        drop_forward_state();
+        return false;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    LensBuildParams params = p;
+    unsigned cap = kUndecidedCap;
+    void *args[] = {&params, &fwd_->grid, &fwd_->status, &fwd_->undecided, &fwd_->counters, &cap};
+    const unsigned block = 128;
+    cudaEventRecord(e0, nullptr);
+    CUresult cr = d.LaunchKernel(m->fn, static_cast<unsigned>((n1 + block - 1) / block), static_cast<unsigned>(n1), static_cast<unsigned>(p.numplates), block, 1, 1, 0,
+                                 nullptr, args, nullptr);
+    cudaEventRecord(e1, nullptr);
+    unsigned counters[16] = {};
+    bool ok = cr == CUDA_SUCCESS;
+    if (!ok) *err = "cuLaunchKernel failed (CUresult " + std::to_string(static_cast<int>(cr)) + ")";
+    if (ok) {
+        ce = cudaMemcpy(counters, fwd_->counters, sizeof counters, cudaMemcpyDeviceToHost);  // synchronises
+        if (ce != cudaSuccess) {
+            *err = std::string("lens kernel: ") + cudaGetErrorString(ce);
+            ok = false;
+        }
+    }
+    if (ok && counters[0] > kUndecidedCap) {
+        *err = "too many grid points need the interpreter (" + std::to_string(counters[0]) + ")";
+        ok = false;
+    }
+    if (ok) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        kernel_ms_ = ms;
+        ++launches_;
+        fwd_->nil_count = counters[1];
+        undecided->resize(counters[0]);
+        if (counters[0]) cudaMemcpy(undecided->data(), fwd_->undecided, counters[0] * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (!ok) drop_forward_state();
+    return ok;
+}
+
+bool LensDevice::forward_finish(const std::vector<ForwardPatch> &patches, int32_t *idx, uint8_t *tint, int display[6],
+                                std::vector<std::pair<uint32_t, int>> *messages, std::string *err) {
+    if (!fwd_) {
+        *err = "forward_finish without forward_points";
+        return false;
+    }
+    const LensBuildParams &p = fwd_->p;
+    const size_t npix = static_cast<size_t>(p.width) * p.height;
+    ForwardPatch *d_patches = nullptr;
+    unsigned *d_keys = nullptr;  // idxkey[npix] then tintkey[npix]
+    uint2 *d_messages = nullptr;
+    int32_t *d_idx = nullptr;
+    uint8_t *d_tint = nullptr;
+    cudaError_t ce = cudaMalloc(&d_keys, 2 * npix * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMemset(d_keys, 0, 2 * npix * sizeof(unsigned));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_messages, kMessageCap * sizeof(uint2));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_idx, npix * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_tint, npix);
+    bool any_nil = fwd_->nil_count > 0;
+    if (ce == cudaSuccess && !patches.empty()) {
+        ce = cudaMalloc(&d_patches, patches.size() * sizeof(ForwardPatch));
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_patches, patches.data(), patches.size() * sizeof(ForwardPatch), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) {
+            const unsigned n = static_cast<unsigned>(patches.size());
+            fwd_patch_kernel<<<(n + 255) / 256, 256>>>(fwd_->grid, fwd_->status, d_patches, n);
+            ++launches_;
+        }
+        for (const ForwardPatch &pt : patches) any_nil = any_nil || pt.status != 1;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (ce == cudaSuccess) {
+        cudaEventRecord(e0, nullptr);
+        if (any_nil) {
+            const int threads = 2 * (p.platesize + 1);
+            fwd_stale_kernel<<<(threads + 63) / 64, 64>>>(fwd_->grid, fwd_->status, p.platesize, p.numplates);
+            ++launches_;
+        }
+        FwdGeom g;
+        g.width = p.width;
+        g.height = p.height;
+        g.ps = p.platesize;
+        g.numplates = p.numplates;
+        g.rubix_block = p.rubix_block;
+        g.rubix_pad = p.rubix_pad;
+        g.rubix_unit_px = p.rubix_unit_px;
+        memcpy(g.plates, p.plates, sizeof g.plates);
+        FwdOut o{d_keys, d_keys + npix, fwd_->counters, d_messages};
+        dim3 grid((p.platesize + 127) / 128, p.platesize, p.numplates);
+        fwd_raster_kernel<<<grid, 128>>>(g, fwd_->grid, o);
+        fwd_resolve_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256>>>(d_keys, d_keys + npix, d_idx, d_tint, npix, p.platesize);
+        launches_ += 2;
+        cudaEventRecord(e1, nullptr);
+        ce = cudaMemcpy(idx, d_idx, npix * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(tint, d_tint, npix, cudaMemcpyDeviceToHost);
+    }
+    unsigned counters[16] = {};
+    if (ce == cudaSuccess) ce = cudaMemcpy(counters, fwd_->counters, sizeof counters, cudaMemcpyDeviceToHost);
+    bool ok = ce == cudaSuccess;
+    if (!ok) *err = std::string("forward lensmap kernels: ") + cudaGetErrorString(ce);
+    if (ok && counters[2] > kMessageCap) {
+        *err = "too many 'maxdiff' messages to replay (" + std::to_string(counters[2]) + ")";
+        ok = false;
+    }
+    if (ok) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        kernel_ms_ += ms;
+        for (int i = 0; i < 6; ++i) display[i] = counters[3 + i] ? 1 : 0;
+        std::vector<uint2> msg(counters[2]);
+        if (counters[2]) cudaMemcpy(msg.data(), d_messages, counters[2] * sizeof(uint2), cudaMemcpyDeviceToHost);
+        messages->clear();
+        for (const uint2 &m : msg) messages->emplace_back(m.x, static_cast<int>(m.y));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_patches);
+    cudaFree(d_keys);
+    cudaFree(d_messages);
+    cudaFree(d_idx);
+    cudaFree(d_tint);
+    drop_forward_state();
     return ok;
 }
 

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace blinky {
@@ -38,18 +39,44 @@ constexpr uint32_t kCandValid = 0x80000000u;   // maps to a texel (bits 0..27 = 
 constexpr uint32_t kCandOnGrid = 0x40000000u;  // rubix padding: the pixel keeps its previous tint
 constexpr uint32_t kCandRisk = 0x20000000u;    // not provably identical to the host result
 
-class LensDevice {
+// a grid point of the forward builder the host evaluated itself
+struct ForwardPatch {
+    uint32_t point;   // (plate * (ps+1) + j) * (ps+1) + i
+    int32_t status;   // 1 = values, 0 = lens_forward returned nil
+    int32_t lx, ly;
+};
+
+// What FisheyeHost needs from a GPU (implemented by LensDevice; faked by nothing: CPU-only
+// contexts simply have no builder and take the interpreter).
+class DeviceLensBuilder {
+public:
+    virtual ~DeviceLensBuilder() {}
+    // inverse lenses: one candidate entry per screen pixel
+    virtual bool build(const std::string &lens_source, const LensBuildParams &p, uint32_t *cand, std::string *err) = 0;
+    // forward lenses, step 1: screen position of every plate grid point; `undecided` receives
+    // the points the host has to evaluate itself
+    virtual bool forward_points(const std::string &lens_source, const LensBuildParams &p, std::vector<uint32_t> *undecided, std::string *err) = 0;
+    // step 2: host results patched in, quads rasterised in the reference's order (last writer
+    // wins), map resolved.  messages: (order key, value) of every "%d > maxdiff" the reference prints.
+    virtual bool forward_finish(const std::vector<ForwardPatch> &patches, int32_t *idx, uint8_t *tint, int display[6],
+                                std::vector<std::pair<uint32_t, int>> *messages, std::string *err) = 0;
+};
+
+class LensDevice : public DeviceLensBuilder {
 public:
     explicit LensDevice(int device) : device_(device) {}
-    ~LensDevice();
+    ~LensDevice() override;
 
     // lens_source = transpile_prelude(true) + TranspileResult::source.
     // Fills cand[width*height].  Returns false (reason in *err) when NVRTC is unavailable,
     // the source does not compile, or a CUDA call fails.
-    bool build(const std::string &lens_source, const LensBuildParams &p, uint32_t *cand, std::string *err);
+    bool build(const std::string &lens_source, const LensBuildParams &p, uint32_t *cand, std::string *err) override;
+    bool forward_points(const std::string &lens_source, const LensBuildParams &p, std::vector<uint32_t> *undecided, std::string *err) override;
+    bool forward_finish(const std::vector<ForwardPatch> &patches, int32_t *idx, uint8_t *tint, int display[6],
+                        std::vector<std::pair<uint32_t, int>> *messages, std::string *err) override;
 
     // compile only (no GPU needed): used by the CPU test-suite and by build()
-    static bool compile(const std::string &lens_source, std::vector<char> *cubin, std::string *log);
+    static bool compile(const std::string &lens_source, bool forward, std::vector<char> *cubin, std::string *log);
 
     double last_compile_ms() const { return compile_ms_; }
     double last_kernel_ms() const { return kernel_ms_; }
@@ -57,8 +84,12 @@ public:
 
 private:
     struct Module;
+    struct ForwardState;
+    Module *module_for(const std::string &lens_source, bool forward, std::string *err);
+    void drop_forward_state();
     int device_;
-    std::map<std::string, Module *> cache_;  // by source text
+    std::map<std::string, Module *> cache_;  // by flavour + source text
+    ForwardState *fwd_ = nullptr;
     double compile_ms_ = 0, kernel_ms_ = 0;
     int64_t launches_ = 0;
 };

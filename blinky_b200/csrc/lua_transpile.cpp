@@ -68,19 +68,20 @@ class Transpiler {
 public:
     explicit Transpiler(State &L) : L_(L) { collect_builtins(); }
 
-    TranspileResult run(const Value &entry) {
+    TranspileResult run(const Value &entry, int nparams, int nresults, const char *what) {
         TranspileResult r;
         try {
-            if (!entry.is_function()) fail("lens_inverse is not a function");
+            const std::string name = what;
+            if (!entry.is_function()) fail(name + " is not a function");
             const Function *fn = static_cast<const Function *>(entry.obj());
-            if (fn->cfn) fail("lens_inverse is a C function");
-            if (fn->proto->nparams != 2 || fn->proto->is_vararg) fail("lens_inverse must take exactly (x, y)");
+            if (fn->cfn) fail(name + " is a C function");
+            if (fn->proto->nparams != nparams || fn->proto->is_vararg) fail(name + " must take exactly " + std::to_string(nparams) + " arguments");
             // pass 1: which script-level variables does the lens assign?
             std::set<const Function *> seen;
             scan_function(fn, seen);
             entry_fn_ = fn;
             FuncInfo &fi = gen_function(fn);
-            if (fi.arity != 3) fail("lens_inverse must return three numbers (or nil)");
+            if (fi.arity != nresults) fail(name + " must return " + (nresults == 3 ? std::string("three") : std::to_string(nresults)) + " numbers (or nil)");
             std::ostringstream o;
             o << "LT_FN void lt_init_mut(Ctx &c) {\n    (void)c;\n";
             for (size_t i = 0; i < mutable_init_.size(); ++i) o << "    c.mg[" << i << "] = LtD(" << num_literal(mutable_init_[i]) << ");\n";
@@ -88,7 +89,11 @@ public:
             if (mutable_init_.size() > 32) fail("too many script-level variables are assigned by the lens");
             o << tables_.str();
             for (const std::string &c : order_) o << c << "\n";
-            o << "LT_FN bool lt_entry(Ctx &c, double x, double y, LtD *r) { return " << fi.cname << "(c, x, y, r); }\n";
+            o << "LT_FN bool lt_entry(Ctx &c";
+            for (int i = 0; i < nparams; ++i) o << ", double a" << i;
+            o << ", LtD *r) { return " << fi.cname << "(c";
+            for (int i = 0; i < nparams; ++i) o << ", a" << i;
+            o << ", r); }\n";
             r.ok = true;
             r.source = o.str();
             r.num_functions = static_cast<int>(order_.size());
@@ -936,7 +941,12 @@ private:
 
 TranspileResult transpile_lens(State &L, const Value &lens_inverse) {
     Transpiler t(L);
-    return t.run(lens_inverse);
+    return t.run(lens_inverse, 2, 3, "lens_inverse");
+}
+
+TranspileResult transpile_lens_forward(State &L, const Value &lens_forward) {
+    Transpiler t(L);
+    return t.run(lens_forward, 3, 2, "lens_forward");
 }
 
 std::string transpile_prelude(bool cuda) {

@@ -33,7 +33,7 @@ namespace blinky {
 struct TranspileResult {
     bool ok = false;
     std::string error;       // why the script is not transpilable
-    std::string source;      // definitions; entry point: bool lt_entry(Ctx &c, double x, double y, double *r)
+    std::string source;      // definitions; entry point: bool lt_entry(Ctx &c, double a0, double a1, LtD *r)
     int num_functions = 0;
     int num_mutable = 0;     // script-level variables the lens assigns (become per-pixel state)
 };
@@ -41,6 +41,8 @@ struct TranspileResult {
 // names of the host-provided script functions (latlon_to_ray, ray_to_latlon, plate_to_ray)
 // are resolved through the State's current globals; `numplates` plates are baked in for plate_to_ray.
 TranspileResult transpile_lens(minilua::State &L, const minilua::Value &lens_inverse);
+// the same for lens_forward(x, y, z) -> x, y; entry point: bool lt_entry(Ctx &c, double a0, double a1, double a2, LtD *r)
+TranspileResult transpile_lens_forward(minilua::State &L, const minilua::Value &lens_forward);
 
 // Support code the generated source needs.  cuda = true: __device__ functions; false: plain C++.
 std::string transpile_prelude(bool cuda);

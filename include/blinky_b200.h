@@ -135,8 +135,9 @@ int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, 
 /* e.g. "device: 12 of 8294400 pixels re-evaluated by the interpreter; NVRTC 310 ms, kernel 1.9 ms"
  * or "host (line 22: nil values are not supported here)" */
 const char *blinky_build_info(blinky_ctx *ctx);
-/* Translate + NVRTC-compile the current lens without running it (works without a GPU). */
-int blinky_compile_lens(blinky_ctx *ctx, size_t *cubin_bytes);
+/* Translate + NVRTC-compile the current lens_inverse (forward = 0) or lens_forward (forward = 1)
+ * kernel without running it (works without a GPU). */
+int blinky_compile_lens(blinky_ctx *ctx, int forward, size_t *cubin_bytes);
 /* 1 if a lens/globe/zoom/rubixgrid/size change since the last build requires a rebuild (:730) */
 int blinky_needs_rebuild(blinky_ctx *ctx, int width, int height, int platesize);
 
@@ -176,10 +177,11 @@ int64_t blinky_mapped_pixels(blinky_ctx *ctx);        /* M in the 5*W*H + M byte
  * return 1 = values, 0 = nil, negative = error */
 int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]);
 int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y);
-/* The current lens_inverse translated to C++ (cuda=0) or CUDA C++ (cuda=1) — what the device
- * lensmap builder compiles.  Returns the bytes needed (excluding NUL), or
- * BLINKY_E_SCRIPT when the lens is outside the translatable subset (reason: blinky_last_error). */
-int blinky_lens_source(blinky_ctx *ctx, int cuda, char *buf, size_t bufsize);
+/* The current lens function translated to C++ / CUDA C++ — what the device lensmap builder
+ * compiles.  flavour: bit 0 = CUDA (else plain C++), bit 1 = lens_forward (else
+ * lens_inverse).  Returns the bytes needed (excluding NUL), or BLINKY_E_SCRIPT when the lens is
+ * outside the translatable subset (reason: blinky_last_error). */
+int blinky_lens_source(blinky_ctx *ctx, int flavour, char *buf, size_t bufsize);
 /* F_WriteConfig text; returns bytes needed (excluding NUL) */
 int blinky_write_config(blinky_ctx *ctx, char *buf, size_t bufsize);
 

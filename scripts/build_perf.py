@@ -8,7 +8,8 @@ import blinky_b200 as bb
 W, H, PS = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (3840, 2160, 2048)
 fe = bb.Fisheye(device=0, palette=bb.synthetic_palette())
 print(f"usable cpus {bb.usable_cpus()}  size {W}x{H} ps {PS}")
-for lens in ["panini", "stereographic", "equirect", "hammer", "fisheye1", "mollweide", "vandergrinten", "winkeltripel", "eckert4", "quincuncial", "cube"]:
+LENSES = [a for a in sys.argv[4:] if not a.startswith("--")] or ["panini", "stereographic", "equirect", "hammer", "fisheye1", "mollweide", "vandergrinten", "winkeltripel", "eckert4", "quincuncial", "cube"]
+for lens in LENSES:
     fe.command("f_globe cube"); fe.command(f"f_lens {lens}")
     t = time.time(); fe.build_lensmap(W, H, PS, threads=0); t_first = time.time() - t
     info = fe.build_info

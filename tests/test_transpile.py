@@ -29,6 +29,18 @@ extern "C" int lt_eval(double x, double y, const LtPlate *plates, int np, double
 }
 """
 
+WRAP_FWD = r"""
+extern "C" int lt_eval_fwd(double a0, double a1, double a2, double *r, unsigned *flag) {
+    Ctx c; c.flag = 0; c.steps = 0; c.plates = 0; c.numplates = 0;
+    lt_init_mut(c);
+    LtD o[2];
+    bool ok = lt_entry(c, a0, a1, a2, o);
+    if (ok) for (int i = 0; i < 2; ++i) { r[i] = o[i].v; r[2 + i] = o[i].e; }
+    *flag = c.flag;
+    return ok ? 1 : 0;
+}
+"""
+
 # lenses that must translate (closed-form and iterative alike); the rest of the shipped set is
 # forward-only (no lens_inverse) or uses nil tests (debug) and takes the interpreter
 TRANSLATABLE = ["cube", "cubestereo", "cylinder", "eckert4", "equirect", "fahey", "fisheye1", "fisheye2", "gallstereo",
@@ -44,17 +56,20 @@ def _points(n_random=700):
     return pts
 
 
-def _compile_host(src, path):
+def _compile_host(src, path, wrap=WRAP):
     cpp = path + ".cpp"
     with open(cpp, "w") as f:
-        f.write(src + WRAP)
+        f.write(src + wrap)
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", path + ".so", cpp],
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[:3000]
     lib = ctypes.CDLL(path + ".so")
-    lib.lt_eval.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
-                            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint)]
+    if wrap is WRAP:
+        lib.lt_eval.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint)]
+    else:
+        lib.lt_eval_fwd.argtypes = [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint)]
     return lib
 
 
@@ -80,6 +95,30 @@ def test_translated_lens_is_bit_identical_to_the_interpreter(host, tmp_path, len
         flagged += bool(flag.value)
     # the error bounds must not degenerate into "everything is uncertain"
     assert flagged <= 0.12 * len(pts), (lens, flagged, len(pts))
+
+
+FORWARD_LENSES = [l for l in ALL_LENSES if l not in ("debug", "quincuncial")]  # every shipped lens_forward
+FORWARD_ONLY = ["eckert1", "eckert5", "gins8", "kavrayskiy7", "larrivee", "polyconic", "sinusoidal", "wagner6", "winkel1", "winkel2"]
+
+
+@pytest.mark.parametrize("lens", FORWARD_LENSES)
+def test_translated_lens_forward_is_bit_identical_to_the_interpreter(host, tmp_path, lens):
+    host.command("f_globe cube")
+    host.command(f"f_lens {lens}")
+    lib = _compile_host(host.lens_source(cuda=False, forward=True), str(tmp_path / lens), WRAP_FWD)
+    rng = np.random.default_rng(11)
+    rays = rng.normal(size=(900, 3))
+    rays /= np.linalg.norm(rays, axis=1, keepdims=True)
+    rays = rays.astype(np.float32).astype(np.float64)  # the builder feeds float32 rays
+    rays = np.vstack([rays, [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [0, -1, 0], [-1, 0, 0]]])
+    out = (ctypes.c_double * 4)()
+    flag = ctypes.c_uint()
+    for rx, ry, rz in rays:
+        st, xy = host.lens_forward(rx, ry, rz)
+        st2 = lib.lt_eval_fwd(rx, ry, rz, out, ctypes.byref(flag))
+        assert st == st2, (lens, rx, ry, rz)
+        if st == 1:
+            assert struct.pack("2d", *xy) == struct.pack("2d", out[0], out[1]), (lens, rx, ry, rz, xy, list(out[:2]))
 
 
 def test_untranslatable_lenses_say_why(bb, host):
@@ -146,6 +185,8 @@ def test_cuda_flavour_compiles_for_sm100a(host, lens):
             pytest.skip(str(e))
         raise
     assert size > 1000
+    if lens != "quincuncial":  # the forward flavour (grid-point kernel of the forward builder)
+        assert host.compile_lens(forward=True) > 1000
 
 
 def test_threads_zero_without_gpu_uses_the_interpreter(host):
@@ -241,3 +282,61 @@ def test_device_build_full_size_matches_golden_c1(bb, fe):
     idx, tint = fe.lensmap()
     c1 = np.load(os.path.join(G, "c1.npz"))
     assert np.array_equal(idx, c1["idx"]) and np.array_equal(tint, c1["tint"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lens", FORWARD_ONLY)
+def test_device_forward_builder_equals_interpreter_build(bb, fe, lens):
+    """forward-only lenses: grid points on the GPU, quads rasterised on the GPU in the reference's
+    writer order (last writer wins, tints stick) == the host's serial scanline builder"""
+    for globe, (w, h, ps), rubix in [("cube", (320, 200, 96), False), ("tetra", (200, 131, 64), True)]:
+        fe.command(f"f_globe {globe}")
+        fe.command(f"f_lens {lens}")
+        fe.set_rubix(rubix)
+        fe.clear_log()
+        fe.build_lensmap(w, h, ps, threads=0)
+        info = fe.build_info
+        assert info.startswith("device (forward):"), (lens, globe, info)
+        dev_idx, dev_tint = fe.lensmap()
+        dev_disp, dev_log = fe.display(), fe.log
+        fe.clear_log()
+        fe.build_lensmap(w, h, ps, threads=1)
+        assert fe.build_info.startswith("host")
+        idx, tint = fe.lensmap()
+        assert np.array_equal(dev_idx, idx), (lens, globe, int((dev_idx != idx).sum()), info)
+        assert np.array_equal(dev_tint, tint), (lens, globe, info)
+        assert dev_disp == fe.display()
+        assert dev_log == fe.log  # the "%d > maxdiff" console messages, in order
+
+
+@pytest.mark.gpu
+def test_device_forward_builder_with_nil_results(bb, fe):
+    """lens_forward returning nil leaves stale row-buffer values behind in the reference; the device
+    replays that, including the px == 0 `continue` that also skips the next slot"""
+    src = """
+    map = "lens_forward"
+    max_fov = 360
+    max_vfov = 180
+    lens_width = 2*pi
+    lens_height = pi
+    onload = "f_contain"
+    function lens_forward(x, y, z)
+      local lat, lon = ray_to_latlon(x, y, z)
+      if lat > 0.9 or (lon > 0.5 and lon < 0.7) or x*x < 0.0004 then
+        return nil
+      end
+      return lon, lat
+    end
+    """
+    for globe, (w, h, ps) in [("cube", (256, 128, 64)), ("trism", (199, 100, 48))]:
+        fe.command(f"f_globe {globe}")
+        fe.load_lens("holes", src)
+        fe.clear_log()
+        fe.build_lensmap(w, h, ps, threads=0)
+        assert fe.build_info.startswith("device (forward):"), fe.build_info
+        a = fe.lensmap_packed().copy()
+        log_a = fe.log
+        fe.clear_log()
+        fe.build_lensmap(w, h, ps, threads=1)
+        assert np.array_equal(a, fe.lensmap_packed()), int((a != fe.lensmap_packed()).sum())
+        assert log_a == fe.log
