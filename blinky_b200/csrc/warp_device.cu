@@ -560,6 +560,32 @@ inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 // ---------------------------------------------------------------------------
 // frame pipeline slot
 // ---------------------------------------------------------------------------
+// ---- host -> device plate upload without the copy engine --------------------------------------
+// The rectangles a lens samples are strided (e.g. half a plate wide); 2-D DMA copies of them reach
+// ~35 GB/s here while the link does 45-48.  Pinned host memory is mapped into the device address
+// space (UVA), so the SMs can pull exactly those bytes themselves, 16 bytes per thread.
+struct UploadRects {
+    int n;
+    uint32_t off[6];     // byte offset of the rectangle's first 16-byte column in the frame
+    uint32_t vec_w[6];   // rectangle width in 16-byte vectors
+    uint32_t rows[6];
+    uint32_t first[7];   // prefix sum of vec_w * rows
+    uint32_t pitch;      // platesize
+};
+
+__global__ void __launch_bounds__(256) upload_rects_kernel(const uint8_t *__restrict__ host_src, uint8_t *__restrict__ dst, const __grid_constant__ UploadRects R) {
+    const uint32_t total = R.first[R.n];
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+        int k = 0;
+        while (v >= R.first[k + 1]) ++k;
+        const uint32_t local = v - R.first[k];
+        const uint32_t row = local / R.vec_w[k], col = local - row * R.vec_w[k];
+        const size_t at = static_cast<size_t>(R.off[k]) + static_cast<size_t>(row) * R.pitch + static_cast<size_t>(col) * 16;
+        const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(host_src + at));
+        *reinterpret_cast<uint4 *>(dst + at) = x;
+    }
+}
+
 struct WarpDevice::Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -610,6 +636,8 @@ WarpDevice::WarpDevice(int device) : device_(device) {
         throw std::runtime_error(buf);
     }
     sm_count_ = prop.multiProcessorCount;
+    if (const char *e = getenv("BLINKY_E2E_UPLOAD")) upload_by_kernel_ = strcmp(e, "kernel") == 0;
+    if (const char *e = getenv("BLINKY_E2E_OUT")) out_by_kernel_ = strcmp(e, "direct") == 0;
     cudaStream_t s;
     e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -953,7 +981,11 @@ bool WarpDevice::launch_flat(const void *d_faces, size_t face_stride, void *d_ou
 
 bool WarpDevice::ensure_slots() {
     if (!slots_.empty()) return true;
-    const int kSlots = 3;
+    int kSlots = 3;
+    if (const char *e = getenv("BLINKY_HOST_SLOTS")) {  // pipeline depth of blinky_warp_host (experiments)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 16) kSlots = v;
+    }
     slot_face_bytes_ = static_cast<size_t>(numplates_) * platesize_ * platesize_;
     slot_out_bytes_ = round_up(npix_, 16);
     for (int i = 0; i < kSlots; ++i) {
@@ -1024,10 +1056,24 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
         // Only what the lens looks at is uploaded: plates with display != 0 (:764-766), and of
         // those only the texel rectangle the lensmap samples.  (TMA boxes may overhang the
         // rectangle; those texels are staged but never referenced by an entry.)
+        UploadRects ur;
+        ur.n = 0;
+        ur.first[0] = 0;
+        ur.pitch = static_cast<uint32_t>(platesize_);
+        const bool by_kernel = upload_by_kernel_ && platesize_ % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 && face_stride % 16 == 0;
         for (int pl = 0; pl < numplates_; ++pl) {
             if (!display_[pl]) continue;
             const int *r = plate_rect_[pl];
             if (r[0] > r[2] || r[1] > r[3]) continue;
+            if (by_kernel && src_pinned) {
+                const int xa = r[0] & ~15, xb = (r[2] + 16) & ~15;  // 16-byte columns covering [r0, r2]
+                ur.off[ur.n] = static_cast<uint32_t>(pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + xa);
+                ur.vec_w[ur.n] = static_cast<uint32_t>((xb - xa) / 16);
+                ur.rows[ur.n] = static_cast<uint32_t>(r[3] - r[1] + 1);
+                ur.first[ur.n + 1] = ur.first[ur.n] + ur.vec_w[ur.n] * ur.rows[ur.n];
+                ++ur.n;
+                continue;
+            }
             const size_t rw = static_cast<size_t>(r[2] - r[0] + 1), rh = static_cast<size_t>(r[3] - r[1] + 1);
             const size_t off = pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + r[0];
             const uint8_t *from = src + off;
@@ -1039,16 +1085,28 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
                                               cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
         }
+        if (ok && ur.n > 0) {
+            const uint32_t total = ur.first[ur.n];
+            const unsigned blocks = std::min<unsigned>((total + 255) / 256, static_cast<unsigned>(sm_count_) * 8u);
+            upload_rects_kernel<<<blocks, 256, 0, s.stream>>>(src, s.d_faces, ur);
+            ++launches_;
+        }
         if (!ok) break;
-        if (!warp(s.d_faces, slot_face_bytes_, s.d_out, slot_out_bytes_, 1, s.stream, false)) { ok = false; break; }
         s.dst = dst_host + static_cast<size_t>(f) * dst_frame_stride;
+        // the warp kernel can store straight into the caller's pinned frame (posted PCIe writes, no
+        // staging copy) when the frame is tightly packed
+        const bool zero_copy_out = out_by_kernel_ && dst_pinned && !keep_unmapped && dst_rowbytes == W && x0 == 0 && y0 == 0 &&
+                                   reinterpret_cast<uintptr_t>(s.dst) % 16 == 0;
+        if (!warp(s.d_faces, slot_face_bytes_, zero_copy_out ? s.dst : s.d_out, slot_out_bytes_, 1, s.stream, false)) { ok = false; break; }
         s.dst_rowbytes = dst_rowbytes;
         s.x0 = x0;
         s.y0 = y0;
         s.keep_unmapped = keep_unmapped;
         s.direct = dst_pinned && !keep_unmapped;
         cudaError_t e;
-        if (s.direct) {
+        if (zero_copy_out) {
+            e = cudaSuccess;
+        } else if (s.direct) {
             e = cudaMemcpy2DAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, static_cast<size_t>(dst_rowbytes), s.d_out,
                                   static_cast<size_t>(W), static_cast<size_t>(W), static_cast<size_t>(H), cudaMemcpyDeviceToHost, s.stream);
         } else {

@@ -72,6 +72,7 @@ private:
     int device_ = 0;
     int sm_count_ = 148;
     void *stream_ = nullptr;  // cudaStream_t
+    bool upload_by_kernel_ = false, out_by_kernel_ = false;  // warp_host variants (BLINKY_E2E_UPLOAD / BLINKY_E2E_OUT)
     std::string err_;
 
     // resident lensmap
