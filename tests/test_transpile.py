@@ -135,6 +135,9 @@ def test_untranslatable_lenses_say_why(bb, host):
         ("local function r(n) if n < 1 then return 1 end return r(n-1) end function lens_inverse(x,y) return x,y,r(3) end", "recursive"),
         ("function lens_inverse(x,y) for k,v in pairs({}) do end return x,y,1 end", "for"),
         ("function lens_inverse(x,y,z) return x,y,1 end", "exactly"),
+        ("function lens_inverse(x,y) print(x) return x,y,1 end", "print"),
+        ("function lens_inverse(x,y) return x,y,math.random() end", "unsupported|resolve"),
+        ("function lens_inverse(x,y) local t = x > 0 and 1 or 2 return x,y,t end", "and"),
         ("function lens_inverse(x,y) return x,y end", "three"),
     ]:
         host.load_lens("t", src)
