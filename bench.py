@@ -255,6 +255,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # the JSON line is the only thing on stdout
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from blinky_b200.sharding import frames_for_rank, gather_frames
@@ -362,6 +363,12 @@ def main():
         dist.broadcast_object_list(handle, src=0)
         peer = base if rank == 0 else fe.ipc_open(handle[0])
         mine = peer + rank * F * frame_bytes
+        if rank == 0:  # poison: a store that never lands shows up as 0xEE
+            class _Raw0:
+                __cuda_array_interface__ = {"shape": (world * F * frame_bytes,), "typestr": "|u1", "data": (base, False), "version": 2}
+
+            torch.as_tensor(_Raw0(), device="cuda").fill_(0xEE)
+        barrier()
         for _ in range(3):
             fe.warp(d_faces, mine, nframes=F, stream=stream)
         barrier()
@@ -381,7 +388,25 @@ def main():
             class _Raw:
                 __cuda_array_interface__ = {"shape": (world * F, H, W), "typestr": "|u1", "data": (base, False), "version": 2}
 
-            fused_ok = bool(torch.equal(torch.as_tensor(_Raw(), device="cuda"), gathered))
+            fused_buf = torch.as_tensor(_Raw(), device="cuda")
+            fused_ok = bool(torch.equal(fused_buf, gathered))
+            if not fused_ok:  # say where, and who is right: recompute the frames here with the flat kernel
+                for r in range(world):
+                    a, b = fused_buf[r * F:(r + 1) * F].reshape(-1), gathered[r * F:(r + 1) * F].reshape(-1)
+                    bad = (a != b).nonzero().flatten()
+                    if bad.numel():
+                        gen_r = torch.Generator(device="cuda").manual_seed(1000 + r)
+                        faces_r = torch.randint(0, 256, (F, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen_r)
+                        truth = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
+                        fe.set_kernel(1)
+                        fe.warp(faces_r, truth, nframes=F, stream=stream)
+                        torch.cuda.synchronize()
+                        fe.set_kernel(args.kernel)
+                        t = truth.reshape(-1)
+                        k = int(bad[0])
+                        print(f"[bench] fused != nccl for rank {r}: {bad.numel()} bytes, first at frame {k // npix} pixel {k % npix}: "
+                              f"fused {a[k:k + 4].tolist()} nccl {b[k:k + 4].tolist()} flat-kernel truth {t[k:k + 4].tolist()}; "
+                              f"fused wrong bytes {int((a != t).sum())}, nccl wrong bytes {int((b != t).sum())}", file=sys.stderr)
         gather.update({"fused_ms_per_step": round(fsec * 1e3, 3), "fused_value": round(world * F * npix / fsec / 1e6, 1),
                        "fused_matches_nccl_gather": fused_ok,
                        "fused_how": "warp kernels write their finished frames directly into rank 0's buffer through CUDA-IPC peer "

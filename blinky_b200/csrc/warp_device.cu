@@ -201,6 +201,7 @@ struct TiledParams {
     size_t out_stride;
     uint32_t ntiles, nframes, total;
     int width, height;
+    uint32_t zero;  // always 0, but only the host knows: see stage_release()
 };
 
 struct __align__(128) TiledStage {
@@ -228,8 +229,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // issued right behind eight pending LDS, and the producer's next TMA then raced them).
 // Passing a value computed from every loaded register as an (unused) asm input makes
 // the scoreboard hold the arrive until those loads have landed.
-__device__ __forceinline__ void mbar_release_after(uint64_t *bar, uint32_t loaded_values) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(smem_u32(bar)), "r"(loaded_values) : "memory");
+// Hands a ring stage back to the producer once EVERY lane of the warp has the stage's data in
+// registers.  `mbarrier.arrive` does not wait for shared-memory loads that are still in flight, and
+// when the LSU queue is backed up (slow stores to a peer GPU or to host memory) an LDS can sit there
+// long enough for the producer's next TMA to overwrite the stage under it.  An unused asm operand is
+// not a dependency either — ptxas drops the computation feeding it.  So the loaded values are folded,
+// through a kernel parameter that is always zero but unknown to the compiler, into the barrier's
+// ADDRESS: the warp-wide OR reduction needs every lane's loaded registers, the arrive needs its result.
+__device__ __forceinline__ void stage_release(uint64_t *bar, uint32_t loaded_values, uint32_t zero, uint32_t lane) {
+    const uint32_t dep = __reduce_or_sync(0xffffffffu, loaded_values & zero);
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + dep) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -294,9 +303,8 @@ __device__ __forceinline__ void gather_tile(const TiledParams &p, const uint32_t
     uint32_t e[8], v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] = ent32[(warp * 8 + j) * kTileW + lane];
-    __syncwarp();
     // entries are in registers: the stage can be refilled
-    if (lane == 0) mbar_release_after(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7]);
+    stage_release(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7], p.zero, lane);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         v[j] = 0;
@@ -430,8 +438,7 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
             box_quad<RUBIX, true>(st.box, s_lut, ea, pa, va);
             box_quad<RUBIX, true>(st.box, s_lut, eb, pb, vb);
-            __syncwarp();
-            if (lane == 0) mbar_release_after(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3]);
+            stage_release(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3], p.zero, lane);
             store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
             store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
             continue;
@@ -450,9 +457,7 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             for (int k = 0; k < 4; ++k) pa[k] = pb[k] = 0;
         }
         // everything this warp needs from the stage is in registers: hand the stage back
-        __syncwarp();
-        if (lane == 0)
-            mbar_release_after(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame);
+        stage_release(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
         if (x < width) {
             if (y0 < height) {
                 patch_background(p.bg, pix0, va, pa);
@@ -887,6 +892,7 @@ bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_o
     p.total = ring_tiles * static_cast<uint32_t>(nframes);
     p.width = width_;
     p.height = height_;
+    p.zero = 0;
     const bool rubix = rubix_;
     const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
     if (tiled_ctas_per_sm_[vi] == 0) {
