@@ -123,3 +123,39 @@ def test_ring_pipeline_stress(bb, fe, palette):
             want = torch.where(t_idx >= 0, src, torch.zeros_like(src))
             for o in outs:
                 assert torch.equal(o[f], want), (lens, f)
+
+
+def test_ring_pipeline_under_store_backpressure(bb, fe, palette):
+    """The same batches with the kernel storing straight into mapped pinned HOST memory: stores as
+    slow as a PCIe/NVLink peer makes them back the LSU queue up, which is what exposed a stage being
+    refilled under shared-memory loads that had been issued but not yet served (wrong 32-pixel rows
+    in 68 of 120 launches before stage_release(); first seen as a fused multi-GPU gather that differed
+    from the NCCL gather at 8 GPUs)."""
+    import torch
+
+    W, H, PS, N = 3840, 2160, 2048, 16
+    h_out = fe.alloc_pinned(N * H * W)
+    try:
+        for lens, zoom, rubix in (("panini", "f_fov 180", False), ("quincuncial", "f_cover", True)):
+            fe.command("f_globe cube")
+            fe.command(f"f_lens {lens}")
+            fe.command(zoom)
+            fe.set_rubix(rubix)
+            fe.build_lensmap(W, H, PS, threads=0)
+            gen = torch.Generator(device="cuda").manual_seed(11)
+            d_faces = torch.randint(0, 256, (N, 6, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+            ref = torch.zeros((N, H, W), dtype=torch.uint8, device="cuda")
+            fe.set_kernel(1)  # flat gather kernel: no ring
+            fe.warp(d_faces, ref, nframes=N)
+            torch.cuda.synchronize()
+            fe.set_kernel(0)
+            want = ref.cpu().numpy().reshape(-1)
+            for launch in range(12):
+                h_out[:] = 0xEE
+                fe.warp(d_faces, int(h_out.ctypes.data), nframes=N)
+                torch.cuda.synchronize()
+                assert "tiled" in fe.last_kernel
+                bad = int((h_out != want).sum())
+                assert bad == 0, (lens, launch, bad)
+    finally:
+        fe.free_pinned(h_out)
