@@ -236,8 +236,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // not a dependency either — ptxas drops the computation feeding it.  So the loaded values are folded,
 // through a kernel parameter that is always zero but unknown to the compiler, into the barrier's
 // ADDRESS: the warp-wide OR reduction needs every lane's loaded registers, the arrive needs its result.
+// CONVERGED: every lane executed the same load instructions (no divergence since the stage became
+// visible).  A warp-level load completes as a whole, so lane 0's registers stand for all lanes and the
+// reduction can be skipped.
+template <bool CONVERGED>
 __device__ __forceinline__ void stage_release(uint64_t *bar, uint32_t loaded_values, uint32_t zero, uint32_t lane) {
-    const uint32_t dep = __reduce_or_sync(0xffffffffu, loaded_values & zero);
+    uint32_t dep = loaded_values & zero;
+    if (CONVERGED) __syncwarp();
+    else dep = __reduce_or_sync(0xffffffffu, dep);
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + dep) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -304,7 +310,7 @@ __device__ __forceinline__ void gather_tile(const TiledParams &p, const uint32_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] = ent32[(warp * 8 + j) * kTileW + lane];
     // entries are in registers: the stage can be refilled
-    stage_release(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7], p.zero, lane);
+    stage_release<true>(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7], p.zero, lane);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         v[j] = 0;
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
             box_quad<RUBIX, true>(st.box, s_lut, ea, pa, va);
             box_quad<RUBIX, true>(st.box, s_lut, eb, pb, vb);
-            stage_release(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3], p.zero, lane);
+            stage_release<true>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3], p.zero, lane);
             store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
             store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
             continue;
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             for (int k = 0; k < 4; ++k) pa[k] = pb[k] = 0;
         }
         // everything this warp needs from the stage is in registers: hand the stage back
-        stage_release(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
+        stage_release<false>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
         if (x < width) {
             if (y0 < height) {
                 patch_background(p.bg, pix0, va, pa);
