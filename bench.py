@@ -47,6 +47,7 @@ WORKLOADS = {
     "4k-cube-fisheye1": (3840, 2160, 2048, "cube", "fisheye1", "f_contain", False),
     "c1-640x480": (640, 480, 256, "cube", "panini", "f_fov 180", False),                  # configs[0]
 }
+OUT = sys.stdout
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -222,10 +223,22 @@ def run_reference(args, rank, world):
                              "sample": f"{frames_per_step} frames per step: plate copy into globe.pixels + render_lensmap, "
                                        f"single thread (the reference's loop has no threading)"},
             "e2e": {"value": round(value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Native libraries print there too (NCCL's version banner
+    under NCCL_DEBUG=VERSION, for one), so fd 1 is pointed at stderr and the line goes out through a
+    private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    global OUT
+    OUT = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -255,7 +268,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # the JSON line is the only thing on stdout
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from blinky_b200.sharding import frames_for_rank, gather_frames
@@ -457,7 +469,7 @@ def main():
             line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(WORKLOADS[args.workload])
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     fe.close()
     if world > 1:
         dist.barrier()
