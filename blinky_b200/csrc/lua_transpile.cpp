@@ -329,18 +329,23 @@ private:
         g.fn = fn;
         g.fi = &fi;
         g.is_entry = fn == entry_fn_;
-        std::ostringstream sig;
-        sig << "LT_FN bool " << fi.cname << "(Ctx &c";
         for (size_t i = 0; i < fn->proto->params.size(); ++i) {
             LocalInfo li;
             li.cname = "p" + std::to_string(i) + "_" + sanitize(fn->proto->params[i]->name);
             li.tainted = !g.is_entry;  // only the entry's (x, y) are known to be exact
             g.locals[fn->proto->params[i]] = li;
+        }
+        while (taint_block(g, fn->proto->body)) {
+        }
+        // the signature comes after the fixpoint: a parameter that is assigned an error-carrying value
+        // inside the body has to be an LtD from the start
+        std::ostringstream sig;
+        sig << "LT_FN bool " << fi.cname << "(Ctx &c";
+        for (size_t i = 0; i < fn->proto->params.size(); ++i) {
+            const LocalInfo &li = g.locals[fn->proto->params[i]];
             sig << (li.tainted ? ", LtD " : ", double ") << li.cname;
         }
         sig << ", LtD *r) {";
-        while (taint_block(g, fn->proto->body)) {
-        }
         line(g, "(void)c; (void)r;");
         gen_block(g, fn->proto->body);
         line(g, "return false;");  // falling off the end returns nothing: nil
