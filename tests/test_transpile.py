@@ -345,3 +345,70 @@ def test_device_forward_builder_with_nil_results(bb, fe):
         fe.build_lensmap(w, h, ps, threads=1)
         assert np.array_equal(a, fe.lensmap_packed()), int((a != fe.lensmap_packed()).sum())
         assert log_a == fe.log
+
+
+# ----------------------------------------------------------------------------- soundness of the error bounds
+#
+# On the GPU the only arithmetic that may differ from the host is libm.  That is emulated here on
+# the CPU: in a second build of the same translation every libm result is moved by a pseudo-random
+# -3..+3 ulp ("some other libm").  Wherever that build raises no risk flag, its outcome must be the
+# exact one: same nil/values status and the same float32 ray.  (Flagged points are the interpreter's.)
+
+EXACT_LT_FN = """LT_FN LtD lt_fn(double r, double prop) {
+    /* identical inputs and a NaN / infinite result (domain error, overflow): the same on both sides */
+    if (prop == 0.0 && !(fabs(r) <= 1.79769313486231570815e308)) return LtD(r);
+    return LtD(r, prop + LT_KU * fabs(r));
+}"""
+
+PERTURBED_LT_FN = """LT_FN LtD lt_fn(double r, double prop) {
+    if (prop == 0.0 && !(fabs(r) <= 1.79769313486231570815e308)) return LtD(r);
+    union { double d; unsigned long long u; } b;
+    b.d = r;
+    const unsigned long long h = (b.u ^ (b.u >> 29)) * 0x9E3779B97F4A7C15ull;
+    const long long k = ((long long)((h >> 40) % 7ull) - 3) * PERT_SCALE;   /* -3 .. +3 (x PERT_SCALE) ulp */
+    const unsigned long long frac = b.u & 0x000FFFFFFFFFFFFFull;
+    if (r != 0.0 && frac > 8ull * PERT_SCALE && frac < 0x000FFFFFFFFFFFFFull - 8ull * PERT_SCALE) b.u += k;
+    return LtD(b.d, prop + LT_KU * fabs(b.d));
+}"""
+
+
+def perturbed(src, scale=1):
+    """scale > 1 magnifies both the libm disagreement and the per-call bound by the same factor: the
+    propagation rules are first order, so they must hold at any (small) scale, and at 2^20 ulp the rare
+    events (a float32 rounding boundary inside the error interval) become frequent enough to be tested."""
+    assert EXACT_LT_FN in src, "lt_fn changed: update the test's copy"
+    assert "#define LT_KU (8.0 * LT_U)" in src
+    src = src.replace("#define LT_KU (8.0 * LT_U)", f"#define PERT_SCALE {scale}LL\n#define LT_KU (8.0 * PERT_SCALE * LT_U)")
+    return src.replace(EXACT_LT_FN, PERTURBED_LT_FN)
+
+
+def f32bits(vals):
+    with np.errstate(over="ignore", invalid="ignore"):
+        return np.asarray(vals, np.float64).astype(np.float32).tobytes()
+
+
+def check_bounds_sound(host, lib, pts, what):
+    out = (ctypes.c_double * 8)()
+    flag = ctypes.c_uint()
+    decided = 0
+    for x, y in pts:
+        st, ray = host.lens_inverse(x, y)
+        st2 = lib.lt_eval(x, y, None, 0, out, ctypes.byref(flag))
+        if flag.value:
+            continue  # the interpreter decides this pixel
+        decided += 1
+        assert st == st2, (what, x, y, st, st2)
+        if st == 1:
+            assert f32bits(ray) == f32bits([out[0], out[1], out[2]]), (what, x, y, ray, list(out[:6]))
+    return decided
+
+
+@pytest.mark.parametrize("scale", [1, 1 << 20])
+@pytest.mark.parametrize("lens", [l for l in TRANSLATABLE if l not in ("cube", "cubestereo")])  # those two use plate_to_ray
+def test_error_bounds_are_sound_under_a_different_libm(host, tmp_path, lens, scale):
+    host.command("f_globe cube")
+    host.command(f"f_lens {lens}")
+    lib = _compile_host(perturbed(host.lens_source(cuda=False), scale), str(tmp_path / f"{lens}{scale}"))
+    pts = _points(2500)
+    decided = check_bounds_sound(host, lib, pts, (lens, scale))
+    assert decided >= (0.4 if scale == 1 else 0.05) * len(pts), (lens, scale, decided, len(pts))

@@ -203,3 +203,31 @@ def test_random_lens_translation_is_bit_identical(host, tmp_path, seed):
         assert st == st2, (seed, x, y, src)
         if st == 1:
             assert struct.pack("3d", *ray) == struct.pack("3d", out[0], out[1], out[2]), (seed, x, y, ray, list(out[:3]), src)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_lens_error_bounds_are_sound(host, tmp_path, seed):
+    """the same programs against a build whose libm results are off by up to 3 x 2^20 ulp (bounds
+    scaled alike, see test_transpile.perturbed): wherever no risk flag is raised, the branch taken,
+    the nil/values status and the float32 ray must be the exact ones"""
+    from test_transpile import f32bits, perturbed
+
+    src = Gen(seed).program()
+    host.command("f_globe cube")
+    host.load_lens(f"fuzz{seed}", src)
+    lib = _compile_host(perturbed(host.lens_source(), 1 << 20), str(tmp_path / f"pert{seed}"), WRAP)
+    out = (ctypes.c_double * 8)()
+    flag = ctypes.c_uint()
+    rng = np.random.default_rng(1000 + seed)
+    decided = 0
+    pts = [tuple(rng.uniform(-3, 3, 2)) for _ in range(250)]
+    for x, y in pts:
+        host.load_lens(f"fuzz{seed}", src)
+        st, ray = host.lens_inverse(x, y)
+        st2 = lib.lt_eval(x, y, None, 0, out, ctypes.byref(flag))
+        if flag.value:
+            continue
+        decided += 1
+        assert st == st2, (seed, x, y, st, st2, src)
+        if st == 1:
+            assert f32bits(ray) == f32bits([out[0], out[1], out[2]]), (seed, x, y, ray, list(out[:6]), src)
