@@ -305,12 +305,13 @@ __device__ __forceinline__ void box_quad(const uint8_t *__restrict__ box, const 
 template <bool RUBIX, bool RGBA>
 __device__ __forceinline__ void gather_tile(const TiledParams &p, const uint32_t *__restrict__ ent32, const uint8_t *__restrict__ faces,
                                             const uint8_t *__restrict__ s_lut, const uint32_t *__restrict__ s_rgba, uint8_t *out_frame,
-                                            uint32_t tile_x, uint32_t tile_y, uint32_t warp, uint32_t lane, uint64_t *empty_bar) {
+                                            uint32_t tile_x, uint32_t tile_y, uint32_t warp, uint32_t lane, uint64_t *empty_bar,
+                                            uint32_t stage_words) {
     uint32_t e[8], v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] = ent32[(warp * 8 + j) * kTileW + lane];
     // entries are in registers: the stage can be refilled
-    stage_release<true>(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7], p.zero, lane);
+    stage_release<true>(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7] | stage_words, p.zero, lane);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         v[j] = 0;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
             box_quad<RUBIX, true>(st.box, s_lut, ea, pa, va);
             box_quad<RUBIX, true>(st.box, s_lut, eb, pb, vb);
-            stage_release<true>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3], p.zero, lane);
+            stage_release<true>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
             store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
             store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
             continue;
@@ -456,7 +457,8 @@ __global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const Tile
             box_quad<RUBIX, false>(st.box, s_lut, eb, pb, vb);
         } else if (type == TILE_GATHER) {
             gather_tile<RUBIX, RGBA>(p, reinterpret_cast<const uint32_t *>(st.box), p.faces + static_cast<size_t>(frame) * p.face_stride,
-                                     s_lut, s_rgba, out_frame, d.w & 0xffffu, d.w >> 16, tid >> 5, lane, &empty_bar[stage]);
+                                     s_lut, s_rgba, out_frame, d.w & 0xffffu, d.w >> 16, tid >> 5, lane, &empty_bar[stage],
+                                     d.w | frame);  // the descriptor words read from the stage count too
             continue;
         } else {
 #pragma unroll
