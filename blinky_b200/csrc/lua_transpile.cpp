@@ -620,8 +620,6 @@ private:
             };
             // the interpreter would print once per pixel; a silent device build would change the console output
             if (n == "print") fail("print() inside the lens function", e->line);
-            const std::string T = tin ? "true" : "false";
-            (void)T;
             if (n == "math.abs") { need(1); one(std::string(tin ? "lt_fabs(" : "fabs(") + a[0].code + ")", tin); return res; }
             if (n == "math.sqrt") { need(1); one(std::string(tin ? "lt_sqrt(" : "sqrt(") + a[0].code + ")", tin); return res; }
             if (n == "math.floor" || n == "math.ceil") {
@@ -940,7 +938,6 @@ private:
     std::map<const Table *, std::string> table_names_;
     const Function *entry_fn_ = nullptr;
     int next_local_ = 0;
-    std::string last_call_nilable_;
 };
 
 }  // namespace

@@ -153,7 +153,7 @@ class Gen:
                 names += ["counter", "memo"]
         return names
 
-    def program(self):
+    def program(self, forward=False):
         r = self.r
         head = ["local min, max, floor, ceil = math.min, math.max, math.floor, math.ceil", "local K1 = 0.625", "local K2 = sqrt(2) / 3", "local tab = {0.25, -1.5, 3, 0.125}", "local counter, memo = 0.5"]
         for h in range(r.randint(0, 2)):
@@ -169,6 +169,16 @@ class Gen:
             head += [f"local function h{h}({', '.join(args)})"] + self.lines + ["end"]
             self.helpers.append((f"h{h}", nargs, nres))
         self.lines, self.indent = [], 1
+        if forward:  # lens_forward(x, y, z) -> x, y
+            names = self.block(["x", "y", "z"], 0, 6)
+            if r.random() < 0.4:
+                self.emit(f"if {self.cond(names)} then return nil end")
+            if r.random() < 0.4:
+                lat, lon = self.new_var(), self.new_var()
+                self.emit(f"local {lat}, {lon} = ray_to_latlon(x, y, z)")
+                names += [lat, lon]
+            self.emit(f"return {self.expr(names, 2)}, {self.expr(names, 2)}")
+            return "\n".join(head + ["function lens_forward(x, y, z)"] + self.lines + ["end"])
         if r.random() < 0.5:
             self.emit(f"if {self.cond(['x', 'y'])} then return nil end")
         names = self.block(["x", "y"], 0, 7)
@@ -231,3 +241,26 @@ def test_random_lens_error_bounds_are_sound(host, tmp_path, seed):
         assert st == st2, (seed, x, y, st, st2, src)
         if st == 1:
             assert f32bits(ray) == f32bits([out[0], out[1], out[2]]), (seed, x, y, ray, list(out[:6]), src)
+
+
+@pytest.mark.parametrize("seed", range(100, 120))
+def test_random_lens_forward_translation_is_bit_identical(host, tmp_path, seed):
+    from test_transpile import WRAP_FWD
+
+    src = Gen(seed).program(forward=True)
+    host.command("f_globe cube")
+    host.load_lens(f"fwd{seed}", src)
+    lib = _compile_host(host.lens_source(forward=True), str(tmp_path / f"fwd{seed}"), WRAP_FWD)
+    out = (ctypes.c_double * 4)()
+    flag = ctypes.c_uint()
+    rng = np.random.default_rng(seed)
+    rays = rng.normal(size=(120, 3))
+    rays = (rays / np.linalg.norm(rays, axis=1, keepdims=True)).astype(np.float32).astype(np.float64)
+    for rx, ry, rz in rays:
+        host.load_lens(f"fwd{seed}", src)
+        st, xy = host.lens_forward(rx, ry, rz)
+        assert st in (0, 1), (seed, st, host.log[-300:], src)
+        st2 = lib.lt_eval_fwd(rx, ry, rz, out, ctypes.byref(flag))
+        assert st == st2, (seed, rx, ry, rz, src)
+        if st == 1:
+            assert struct.pack("2d", *xy) == struct.pack("2d", out[0], out[1]), (seed, rx, ry, rz, xy, list(out[:2]), src)
