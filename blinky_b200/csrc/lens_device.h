@@ -7,6 +7,12 @@
 // (fisheye.c:2023-2066, 1922-2013) runs in the same kernel with the host's exact float /
 // double operation order.
 //
+// Forward-only lenses (fisheye.c:2126-2338) get the same treatment:
+// lens_forward is evaluated at every plate grid point by a translated kernel, then static
+// kernels in lens_device.cu replay the reference's stale-slot behaviour, rasterise the quads
+// with the writer order encoded in atomicMax keys (last writer wins, tints stick) and resolve
+// the map.
+//
 // Every pixel whose outcome is not provably identical to what the host's libm would give
 // carries a risk bit and is re-evaluated by the host interpreter (fisheye_host.cpp), so the
 // finished lensmap is the same as the all-host build.
@@ -46,8 +52,8 @@ struct ForwardPatch {
     int32_t lx, ly;
 };
 
-// What FisheyeHost needs from a GPU (implemented by LensDevice; faked by nothing: CPU-only
-// contexts simply have no builder and take the interpreter).
+// What FisheyeHost needs from a GPU (implemented by LensDevice).  CPU-only contexts have no
+// builder and take the interpreter.
 class DeviceLensBuilder {
 public:
     virtual ~DeviceLensBuilder() {}

@@ -123,12 +123,14 @@ int blinky_set_rubixgrid(blinky_ctx *ctx, int numcells, double cell_size, double
  *   threads  > 1  rows are split over that many cloned script states (requires
  *                 lens_inverse to be a pure function of x,y — true for every shipped lens);
  *   threads  < 0  as above with every CPU the process may use;
- *   threads == 0  GPU build: lens_inverse is translated to CUDA, compiled for sm_100a
- *                 with NVRTC and evaluated for all pixels by one kernel; pixels whose
- *                 result is not provably the host's (error bounds on every libm call)
- *                 are re-evaluated by the interpreter, so the map is the same as the
- *                 host build's.  Lenses outside the translatable subset, forward-only
- *                 lenses and CPU-only contexts fall back to threads < 0.
+ *   threads == 0  GPU build: the lens function is translated to CUDA, compiled for sm_100a
+ *                 with NVRTC and evaluated by one kernel — lens_inverse for every screen
+ *                 pixel, or, for forward-only lenses, lens_forward for every plate grid point
+ *                 followed by the quad rasterisation in the reference's writer order.
+ *                 Results that are not provably the host's (error bounds on every libm call)
+ *                 are re-evaluated by the interpreter, so the map is the same as the host
+ *                 build's.  Lenses outside the translatable subset, globes with a
+ *                 globe_plate script and CPU-only contexts fall back to threads < 0.
  * blinky_build_info() says which way the last build went.
  * On a GPU context the packed map, tile table and tint LUTs are uploaded too. */
 int blinky_build_lensmap(blinky_ctx *ctx, int width, int height, int platesize, int threads);
