@@ -329,9 +329,10 @@ class Fisheye:
         st = self._lib.blinky_lens_forward(self._ctx, rx, ry, rz, ctypes.byref(x), ctypes.byref(y))
         return st, (x.value, y.value)
 
-    def lens_source(self, cuda: bool = False, forward: bool = False) -> str:
-        """The current ``lens_inverse`` (or ``lens_forward``) translated to C++/CUDA (raises when not translatable)."""
-        flavour = int(cuda) | (2 if forward else 0)
+    def lens_source(self, cuda: bool = False, forward: bool = False, with_kernel: bool = False) -> str:
+        """The current ``lens_inverse`` (or ``lens_forward``) translated to C++/CUDA (raises when not translatable);
+        ``with_kernel`` appends the fixed kernel the device builder launches."""
+        flavour = int(cuda) | (2 if forward else 0) | (4 if with_kernel else 0)
         n = self._lib.blinky_lens_source(self._ctx, flavour, None, 0)
         if n < 0:
             self._check(n)

@@ -297,6 +297,7 @@ int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double
 int blinky_lens_source(blinky_ctx *ctx, int flavour, char *buf, size_t bufsize) {
     std::string s, why;
     if (!ctx->host.lens_device_source((flavour & 1) != 0, &s, &why, (flavour & 2) != 0)) return set_err(ctx, BLINKY_E_SCRIPT, why);
+    if (flavour & 4) s += LensDevice::kernel_tail((flavour & 2) != 0);
     if (buf && bufsize) {
         size_t n = s.size() < bufsize - 1 ? s.size() : bufsize - 1;
         memcpy(buf, s.data(), n);

@@ -413,6 +413,8 @@ void LensDevice::drop_forward_state() {
     fwd_ = nullptr;
 }
 
+const char *LensDevice::kernel_tail(bool forward) { return forward ? kForwardKernelSource : kKernelSource; }
+
 bool LensDevice::compile(const std::string &lens_source, bool forward, std::vector<char> *cubin, std::string *log) {
     Nvrtc &n = nvrtc();
     if (!n.why.empty()) {

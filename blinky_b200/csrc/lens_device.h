@@ -81,6 +81,10 @@ public:
     bool forward_finish(const std::vector<ForwardPatch> &patches, int32_t *idx, uint8_t *tint, int display[6],
                         std::vector<std::pair<uint32_t, int>> *messages, std::string *err) override;
 
+    // the fixed CUDA source appended to a translated lens (the per-pixel / per-grid-point tail);
+    // exposed so that the CPU test-suite can run the very same text through a host shim
+    static const char *kernel_tail(bool forward);
+
     // compile only (no GPU needed): used by the CPU test-suite and by build()
     static bool compile(const std::string &lens_source, bool forward, std::vector<char> *cubin, std::string *log);
 

@@ -181,7 +181,8 @@ int blinky_lens_inverse(blinky_ctx *ctx, double x, double y, double ray_out[3]);
 int blinky_lens_forward(blinky_ctx *ctx, double rx, double ry, double rz, double *x, double *y);
 /* The current lens function translated to C++ / CUDA C++ — what the device lensmap builder
  * compiles.  flavour: bit 0 = CUDA (else plain C++), bit 1 = lens_forward (else
- * lens_inverse).  Returns the bytes needed (excluding NUL), or BLINKY_E_SCRIPT when the lens is
+ * lens_inverse), bit 2 = append the fixed kernel (the per-pixel / per-grid-point tail) — with
+ * bits 0 and 2 this is exactly what NVRTC is given.  Returns the bytes needed (excluding NUL), or BLINKY_E_SCRIPT when the lens is
  * outside the translatable subset (reason: blinky_last_error). */
 int blinky_lens_source(blinky_ctx *ctx, int flavour, char *buf, size_t bufsize);
 /* F_WriteConfig text; returns bytes needed (excluding NUL) */
