@@ -1,6 +1,7 @@
 // Device-side lensmap construction: NVRTC compile of the translated lens + launch.
 // See lens_device.h.
 #include "lens_device.h"
+#include "forward_raster.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -216,7 +217,7 @@ struct LensDevice::Module {
 struct LensDevice::ForwardState {
     LensBuildParams p;
     size_t npoints = 0;
-    int2 *grid = nullptr;
+    FwdPoint *grid = nullptr;
     unsigned char *status = nullptr;
     unsigned *undecided = nullptr;
     unsigned *counters = nullptr;  // [0] undecided points, [1] nil results, [2] messages, [3..8] display flags
@@ -226,171 +227,31 @@ struct LensDevice::ForwardState {
 namespace {
 
 constexpr unsigned kUndecidedCap = 1u << 20;
-constexpr unsigned kMessageCap = 4096;
+constexpr unsigned kMessageCap = kFwdMessageCap;
 
-// ---- forward builder, steps 2-4 (static kernels; this file is compiled with --fmad=false) ----------
+// ---- forward builder, steps 2-4 (this file is compiled with --fmad=false) ---------------------------
+// The per-thread bodies live in forward_raster.h (host/device) so that the CPU suite can run them
+// — in arbitrary thread orders — against the reference-equivalent serial builder.
 
-struct FwdGeom {
-    int width, height, ps, numplates;
-    double rubix_block, rubix_pad, rubix_unit_px;
-    LensBuildParams::PlateF plates[6];
-};
-
-__global__ void fwd_patch_kernel(int2 *grid, unsigned char *status, const ForwardPatch *patches, unsigned n) {
+__global__ void fwd_patch_kernel(FwdPoint *grid, unsigned char *status, const ForwardPatch *patches, unsigned n) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const ForwardPatch pt = patches[k];
-    status[pt.point] = static_cast<unsigned char>(pt.status);
-    if (pt.status == 1) grid[pt.point] = make_int2(pt.lx, pt.ly);
+    if (k < n) fwd_apply_patch(grid, status, patches[k]);
 }
 
-// The reference keeps two row buffers and `continue`s over nil results (fisheye.c:2151-2189), so a
-// nil slot shows whatever the buffer held before: the row two steps earlier, the previous plate's last
-// rows at a plate start, zero at the very beginning.  One thread per (column, buffer) replays its chain.
-__global__ void fwd_stale_kernel(int2 *grid, const unsigned char *status, int ps, int numplates) {
-    const int n1 = ps + 1;
+__global__ void fwd_stale_kernel(FwdPoint *grid, const unsigned char *status, int ps, int numplates) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n1) return;
-    const int i = t >> 1;
-    int j = (t & 1) ? ps - 1 : ps;  // buffer `bot` starts with row ps, buffer `top` with row ps-1
-    int2 last = make_int2(0, 0);
-    for (int p = 0; p < numplates;) {
-        const size_t row = (static_cast<size_t>(p) * n1 + j) * n1;
-        // slot 1 is skipped together with slot 0 (the `continue` in the px == 0 branch)
-        const bool valid = status[row + i] == 1 && !(i == 1 && status[row] != 1);
-        if (valid) last = grid[row + i];
-        else grid[row + i] = last;
-        if (j >= 2) {
-            j -= 2;
-        } else {
-            j = j == 1 ? ps : ps - 1;  // the buffer that ended as `bot` (row 1) takes row ps of the next plate
-            ++p;
-        }
-    }
+    if (t < 2 * (ps + 1)) fwd_stale_chain(grid, status, ps, numplates, t);
 }
 
-__device__ __forceinline__ float fdot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-
-struct FwdOut {
-    unsigned *idxkey, *tintkey, *counters;
-    uint2 *messages;
-};
-
-__device__ __forceinline__ void fwd_set(const FwdGeom &g, const FwdOut &o, int lx, int ly, unsigned key, bool ongrid, int plate) {
-    if (lx < 0 || lx >= g.width || ly < 0 || ly >= g.height) return;  // set_lensmap_from_plate's screen check
-    o.counters[3 + plate] = 1u;                                         // display flag (benign race: all writers store 1)
-    const size_t at = static_cast<size_t>(lx) + static_cast<size_t>(ly) * g.width;
-    atomicMax(&o.idxkey[at], key);
-    if (!ongrid) atomicMax(&o.tintkey[at], key);
-}
-
-// draw_quad (fisheye.c:2246-2338) for the texel (plate, px, py); key orders the writers like the
-// reference's loops do (plate ascending, py descending, px ascending): the highest key wins.
-__global__ void __launch_bounds__(128) fwd_raster_kernel(const __grid_constant__ FwdGeom g, const int2 *__restrict__ grid, FwdOut o) {
-    const int ps = g.ps, n1 = ps + 1;
-    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, plate = blockIdx.z;
-    if (px >= ps) return;
-    // the texel belongs to this plate only if the plate wins the ray's argmax (:2193-2199)
-    {
-        const LensBuildParams::PlateF &P = g.plates[plate];
-        double u = static_cast<double>(px) / ps, v = static_cast<double>(py) / ps;
-        u -= 0.5;
-        v -= 0.5;
-        v = -v;
-        float r[3] = {0.0f, 0.0f, 0.0f};
-        const float fu = static_cast<float>(u), fv = static_cast<float>(v);
-        for (int k = 0; k < 3; ++k) r[k] = r[k] + P.dist * P.forward[k];
-        for (int k = 0; k < 3; ++k) r[k] = r[k] + fu * P.right[k];
-        for (int k = 0; k < 3; ++k) r[k] = r[k] + fv * P.up[k];
-        float len = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-        len = static_cast<float>(sqrt(static_cast<double>(len)));
-        if (len) {
-            const float inv = 1 / len;
-            r[0] *= inv;
-            r[1] *= inv;
-            r[2] *= inv;
-        }
-        int best = 0;
-        double best_dp = -2;
-        for (int k = 0; k < g.numplates; ++k) {
-            const double dp = static_cast<double>(fdot3(r, g.plates[k].forward));
-            if (dp > best_dp) {
-                best_dp = dp;
-                best = k;
-            }
-        }
-        if (best != plate) return;
-    }
-    const unsigned key = (static_cast<unsigned>(plate) * ps + (ps - 1 - py)) * ps + px + 1u;
-    const double ux = static_cast<double>(px) / g.rubix_unit_px, uy = static_cast<double>(py) / g.rubix_unit_px;
-    const bool ongrid = fmod(ux, g.rubix_block) < g.rubix_pad || fmod(uy, g.rubix_block) < g.rubix_pad;
-
-    const size_t top = (static_cast<size_t>(plate) * n1 + py) * n1, bot = top + n1;
-    const int2 c0 = grid[top + px], c1 = grid[top + px + 1], c2 = grid[bot + px + 1], c3 = grid[bot + px];  // tl, tr, br, bl: clockwise
-    const int cx[4] = {c0.x, c1.x, c2.x, c3.x}, cy[4] = {c0.y, c1.y, c2.y, c3.y};
-    int x = cx[0], y = cy[0];
-    int minx = x, maxx = x, miny = y, maxy = y;
-    for (int i = 1; i < 4; ++i) {
-        if (cx[i] < minx) minx = cx[i]; else if (cx[i] > maxx) maxx = cx[i];
-        if (cy[i] < miny) miny = cy[i]; else if (cy[i] > maxy) maxy = cy[i];
-    }
-    const int maxdiff = 20;
-    // abs() of an int difference, computed like the host does (wraps the same way on overflow)
-    const int ddx = minx - maxx, ddy = miny - maxy;
-    if ((ddx < 0 ? -ddx : ddx) > maxdiff || (ddy < 0 ? -ddy : ddy) > maxdiff) return;
-    if (miny == maxy && minx == maxx) {
-        fwd_set(g, o, x, y, key, ongrid, plate);
-        return;
-    }
-    if (miny == maxy) {
-        for (int tx = minx; tx <= maxx; ++tx) fwd_set(g, o, tx, miny, key, ongrid, plate);
-        return;
-    }
-    if (minx == maxx) {
-        for (int ty = miny; ty <= maxy; ++ty) fwd_set(g, o, x, ty, key, ongrid, plate);
-        return;
-    }
-    for (y = miny; y <= maxy; ++y) {
-        int tx[2] = {minx, maxx};
-        int found = 0;
-        int j = 3;
-        for (int i = 0; i < 4; ++i) {
-            const int ix = cx[i], iy = cy[i], jx = cx[j], jy = cy[j];
-            if ((iy < y && y <= jy) || (jy < y && y <= iy)) {
-                const double dy = jy - iy;
-                const double dx = jx - ix;
-                tx[found] = static_cast<int>(ix + (y - iy) / dy * dx);
-                if (++found == 2) break;
-            }
-            j = i;
-        }
-        if (tx[0] > tx[1]) {
-            const int t = tx[0];
-            tx[0] = tx[1];
-            tx[1] = t;
-        }
-        if (tx[1] - tx[0] > maxdiff) {
-            const unsigned at = atomicAdd(&o.counters[2], 1u);
-            if (at < kMessageCap) o.messages[at] = make_uint2(key, static_cast<unsigned>(tx[1] - tx[0]));
-            return;
-        }
-        for (x = tx[0]; x <= tx[1]; ++x) fwd_set(g, o, x, y, key, ongrid, plate);
-    }
+__global__ void __launch_bounds__(128) fwd_raster_kernel(const __grid_constant__ FwdGeom g, const FwdPoint *__restrict__ grid, FwdOut o) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px < g.ps) fwd_raster_texel(g, grid, o, static_cast<int>(blockIdx.z), static_cast<int>(blockIdx.y), px);
 }
 
 __global__ void fwd_resolve_kernel(const unsigned *__restrict__ idxkey, const unsigned *__restrict__ tintkey, int32_t *__restrict__ idx,
                                    uint8_t *__restrict__ tint, size_t npix, int ps) {
     const size_t at = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (at >= npix) return;
-    const unsigned k = idxkey[at];
-    if (k) {
-        const unsigned key = k - 1, px = key % ps, t = key / ps, py = ps - 1 - t % ps, plate = t / ps;
-        idx[at] = static_cast<int32_t>(plate * ps * ps + py * ps + px);
-    } else {
-        idx[at] = -1;
-    }
-    const unsigned tk = tintkey[at];
-    tint[at] = tk ? static_cast<uint8_t>((tk - 1) / ps / ps) : 255;
+    if (at < npix) fwd_resolve_pixel(idxkey, tintkey, idx, tint, at, ps);
 }
 
 }  // namespace
@@ -549,7 +410,7 @@ bool LensDevice::forward_points(const std::string &lens_source, const LensBuildP
     fwd_ = new ForwardState;
     fwd_->p = p;
     fwd_->npoints = npoints;
-    cudaError_t ce = cudaMalloc(&fwd_->grid, npoints * sizeof(int2));
+    cudaError_t ce = cudaMalloc(&fwd_->grid, npoints * sizeof(FwdPoint));
     if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->status, npoints);
     if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->undecided, kUndecidedCap * sizeof(unsigned));
     if (ce == cudaSuccess) ce = cudaMalloc(&fwd_->counters, 16 * sizeof(unsigned));
@@ -609,12 +470,12 @@ bool LensDevice::forward_finish(const std::vector<ForwardPatch> &patches, int32_
     const size_t npix = static_cast<size_t>(p.width) * p.height;
     ForwardPatch *d_patches = nullptr;
     unsigned *d_keys = nullptr;  // idxkey[npix] then tintkey[npix]
-    uint2 *d_messages = nullptr;
+    FwdMessage *d_messages = nullptr;
     int32_t *d_idx = nullptr;
     uint8_t *d_tint = nullptr;
     cudaError_t ce = cudaMalloc(&d_keys, 2 * npix * sizeof(unsigned));
     if (ce == cudaSuccess) ce = cudaMemset(d_keys, 0, 2 * npix * sizeof(unsigned));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_messages, kMessageCap * sizeof(uint2));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_messages, kMessageCap * sizeof(FwdMessage));
     if (ce == cudaSuccess) ce = cudaMalloc(&d_idx, npix * sizeof(int32_t));
     if (ce == cudaSuccess) ce = cudaMalloc(&d_tint, npix);
     bool any_nil = fwd_->nil_count > 0;
@@ -669,10 +530,10 @@ bool LensDevice::forward_finish(const std::vector<ForwardPatch> &patches, int32_
         cudaEventElapsedTime(&ms, e0, e1);
         kernel_ms_ += ms;
         for (int i = 0; i < 6; ++i) display[i] = counters[3 + i] ? 1 : 0;
-        std::vector<uint2> msg(counters[2]);
-        if (counters[2]) cudaMemcpy(msg.data(), d_messages, counters[2] * sizeof(uint2), cudaMemcpyDeviceToHost);
+        std::vector<FwdMessage> msg(counters[2]);
+        if (counters[2]) cudaMemcpy(msg.data(), d_messages, counters[2] * sizeof(FwdMessage), cudaMemcpyDeviceToHost);
         messages->clear();
-        for (const uint2 &m : msg) messages->emplace_back(m.x, static_cast<int>(m.y));
+        for (const FwdMessage &m : msg) messages->emplace_back(m.key, static_cast<int>(m.value));
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

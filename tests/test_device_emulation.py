@@ -186,3 +186,165 @@ def test_emulated_forward_points_equal_interpreter(host, tmp_path, lens, scale):
             assert want == (int(grid[pt][0]), int(grid[pt][1])), (lens, scale, pt, want, grid[pt].tolist())
     assert decided > 0.3 * npts, (lens, scale, decided, npts)
     assert int(counters[0]) == int((status == 2).sum())
+
+
+# ----------------------------------------------------------------------------- forward builder, steps 2-4
+
+FWD_HARNESS = r"""
+#include <vector>
+#include <cstring>
+#include "forward_raster.h"
+using namespace blinky;
+extern "C" int fwd_sizeof_geom() { return (int)sizeof(FwdGeom); }
+// patches -> stale replay -> rasterise every texel in the order given -> resolve
+extern "C" void fwd_run(const FwdGeom *g, FwdPoint *grid, unsigned char *status, const ForwardPatch *patches, unsigned npatch,
+                        int any_nil, const unsigned *order, unsigned ntexels, int32_t *idx, uint8_t *tint, int *display,
+                        FwdMessage *messages, unsigned *nmsg) {
+    for (unsigned k = 0; k < npatch; ++k) fwd_apply_patch(grid, status, patches[k]);
+    if (any_nil)
+        for (int t = 2 * (g->ps + 1) - 1; t >= 0; --t) fwd_stale_chain(grid, status, g->ps, g->numplates, t);
+    const size_t npix = (size_t)g->width * g->height;
+    std::vector<unsigned> keys(2 * npix, 0u);
+    unsigned counters[16];
+    memset(counters, 0, sizeof counters);
+    FwdOut o{keys.data(), keys.data() + npix, counters, messages};
+    for (unsigned k = 0; k < ntexels; ++k) {
+        const unsigned t = order[k];
+        const int px = t % g->ps, py = t / g->ps % g->ps, plate = t / g->ps / g->ps;
+        fwd_raster_texel(*g, grid, o, plate, py, px);
+    }
+    for (size_t at = 0; at < npix; ++at) fwd_resolve_pixel(keys.data(), keys.data() + npix, idx, tint, at, g->ps);
+    for (int i = 0; i < 6; ++i) display[i] = counters[3 + i] ? 1 : 0;
+    *nmsg = counters[2];
+}
+"""
+
+
+class FwdGeom(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("ps", ctypes.c_int), ("numplates", ctypes.c_int),
+                ("rubix_block", ctypes.c_double), ("rubix_pad", ctypes.c_double), ("rubix_unit_px", ctypes.c_double),
+                ("plates", PlateF * 6)]
+
+
+class ForwardPatch(ctypes.Structure):
+    _fields_ = [("point", ctypes.c_uint32), ("status", ctypes.c_int32), ("lx", ctypes.c_int32), ("ly", ctypes.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def fwd_lib(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fwd")
+    src = d / "fwd_harness.cpp"
+    src.write_text(FWD_HARNESS)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(root, "blinky_b200", "csrc"),
+                        "-o", str(d / "fwd_harness.so"), str(src)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[:3000]
+    lib = ctypes.CDLL(str(d / "fwd_harness.so"))
+    assert lib.fwd_sizeof_geom() == ctypes.sizeof(FwdGeom)
+    return lib
+
+
+def x86_int(v):
+    """(int) of a double as cvttsd2si does it: out of range / NaN -> INT_MIN"""
+    if not math.isfinite(v) or abs(v) >= 2147483648.0:
+        return -2147483648
+    return int(v)
+
+
+HOLES = """
+map = "lens_forward"
+max_fov = 360
+max_vfov = 180
+lens_width = 2*pi
+lens_height = pi
+onload = "f_contain"
+function lens_forward(x, y, z)
+  local lat, lon = ray_to_latlon(x, y, z)
+  if lat > 0.9 or (lon > 0.5 and lon < 0.7) or x*x < 0.0004 then
+    return nil
+  end
+  return lon, lat
+end
+"""
+
+
+@pytest.mark.parametrize("scale", [0, 1 << 20])
+@pytest.mark.parametrize("lens", ["eckert1", "sinusoidal", "winkel2", "polyconic", "larrivee", "holes"])
+def test_emulated_forward_build_equals_serial_builder_in_any_thread_order(host, fwd_lib, tmp_path, lens, scale):
+    """grid points (NVRTC text behind the shim, exact or perturbed libm) -> undecided points from the
+    interpreter -> stale-slot replay -> quads rasterised in RANDOM texel orders with max-key writes ->
+    resolve: must equal the reference-equivalent serial scanline builder, including the display flags
+    and the order of its "> maxdiff" console messages"""
+    host.set_rubixgrid(*GRID)
+    for globe, (w, h, ps) in (("cube", (128, 80, 20)), ("trism", (97, 60, 14))):
+        host.command(f"f_globe {globe}")
+        if lens == "holes":
+            host.load_lens("holes", HOLES)
+        else:
+            host.command(f"f_lens {lens}")
+        host.clear_log()
+        host.build_lensmap(w, h, ps, threads=1)
+        want_idx, want_tint = host.lensmap()
+        want_disp = host.display()
+        want_msgs = [int(l.split()[0]) for l in host.log.splitlines() if l.endswith("> maxdiff")]
+
+        src = host.lens_source(forward=True, with_kernel=True)
+        if scale:
+            src = perturbed(src, scale)
+        lib = build_lib(src, RUN_FORWARD, str(tmp_path / f"{lens}_{globe}_{scale}"))
+        p = params_of(host, w, h, ps)
+        n1 = ps + 1
+        P = host.numplates
+        npts = P * n1 * n1
+        grid = np.zeros((npts, 2), np.int32)
+        status = np.zeros(npts, np.uint8)
+        undecided = np.zeros(npts, np.uint32)
+        counters = np.zeros(16, np.uint32)
+        lib.run_lt_forward_points(ctypes.byref(p), grid.ctypes.data_as(ctypes.c_void_p), status.ctypes.data_as(ctypes.c_void_p),
+                                  undecided.ctypes.data_as(ctypes.c_void_p), counters.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(npts))
+        # the interpreter settles the undecided points (FisheyeHost::build_forward_device)
+        plates = host.plates()
+        und = undecided[: int(counters[0])]
+        patches = (ForwardPatch * max(1, len(und)))()
+        for k, pt in enumerate(und.tolist()):
+            i, j, plate = pt % n1, pt // n1 % n1, pt // n1 // n1
+            f, r, u = (plates[plate][a:a + 3].astype(np.float32) for a in (0, 3, 6))
+            uu = np.float32((i - 0.5) / ps - 0.5)
+            vv = np.float32(-((j - 0.5) / ps - 0.5))
+            ray = np.float32(plates[plate][10]) * f
+            ray = ray + uu * r
+            ray = ray + vv * u
+            ln = np.float32(math.sqrt(float(ray[0] * ray[0] + ray[1] * ray[1] + ray[2] * ray[2])))
+            if ln:
+                ray = ray * (np.float32(1) / ln)
+            st, (x, y) = host.lens_forward(float(ray[0]), float(ray[1]), float(ray[2]))
+            patches[k].point, patches[k].status = pt, st
+            if st == 1:
+                patches[k].lx, patches[k].ly = x86_int(x / host.scale + w // 2), x86_int(-y / host.scale + h // 2)
+        any_nil = int(counters[1] > 0 or any(patches[k].status != 1 for k in range(len(und))))
+
+        g = FwdGeom()
+        g.width, g.height, g.ps, g.numplates = w, h, ps, P
+        g.rubix_block, g.rubix_pad, g.rubix_unit_px = p.rubix_block, p.rubix_pad, p.rubix_unit_px
+        for i in range(6):
+            g.plates[i] = p.plates[i]
+        ntex = P * ps * ps
+        rng = np.random.default_rng(5)
+        for order in (np.arange(ntex), np.arange(ntex)[::-1].copy(), rng.permutation(ntex), rng.permutation(ntex)):
+            order = order.astype(np.uint32)
+            gcopy, scopy = grid.copy(), status.copy()
+            idx = np.zeros(w * h, np.int32)
+            tint = np.zeros(w * h, np.uint8)
+            disp = (ctypes.c_int * 6)()
+            msgs = np.zeros((4096, 2), np.uint32)
+            nmsg = ctypes.c_uint()
+            fwd_lib.fwd_run(ctypes.byref(g), gcopy.ctypes.data_as(ctypes.c_void_p), scopy.ctypes.data_as(ctypes.c_void_p), patches,
+                            ctypes.c_uint(len(und)), any_nil, order.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(ntex),
+                            idx.ctypes.data_as(ctypes.c_void_p), tint.ctypes.data_as(ctypes.c_void_p), disp,
+                            msgs.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nmsg))
+            assert np.array_equal(idx.reshape(h, w), want_idx), (lens, globe, scale, int((idx.reshape(h, w) != want_idx).sum()))
+            assert np.array_equal(tint.reshape(h, w), want_tint), (lens, globe, scale)
+            assert list(disp)[:P] == want_disp[:P], (lens, globe)
+            got_msgs = [int(v) for _, v in sorted(map(tuple, msgs[: nmsg.value].tolist()))]
+            assert got_msgs == want_msgs, (lens, globe, scale)
