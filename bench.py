@@ -161,7 +161,7 @@ def cpu_baseline(workload, threads_all: bool = False):
         out = {"value": round(W * H / best / 1e6, 1), "unit": "Mpixels/s", "cores": 1, "kind": "port",
                "sample": f"{reps} x restated render_lensmap (oracle/blinky_oracle.c) of one {W}x{H} frame, single thread; best call",
                "mean_value": round(W * H * reps / total / 1e6, 1)}
-    nthreads = O.max_threads()
+    nthreads = min(O.max_threads(), bb.usable_cpus())  # the cgroup quota, not the 128 cores the box shows
     bestn, _ = O.time_render(idx, tint, faces, pm, rubix, nthreads, 20)
     out["all_cores_port"] = {"value": round(W * H / bestn / 1e6, 1), "unit": "Mpixels/s", "cores": nthreads,
                              "note": "same loop, rows split over all host threads (oracle port; the reference itself is single-threaded)"}
