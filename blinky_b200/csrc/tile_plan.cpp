@@ -1,6 +1,7 @@
 #include "tile_plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/blinky_b200.h"
@@ -11,7 +12,7 @@ namespace blinky {
 namespace {
 
 // one row of tiles; entry offsets are relative to the row's own entry buffer
-void plan_tile_row(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int ty, TilePlan &plan) {
+void plan_tile_row(const uint32_t *packed, int width, int height, int platesize, bool allow_box, bool odd_pitch, int ty, TilePlan &plan) {
     const uint32_t ps = static_cast<uint32_t>(platesize);
     const uint32_t ps2 = ps * ps;
     std::vector<uint32_t> tile(kTilePixels);
@@ -65,6 +66,12 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
                 bw = ((maxx - minx + 1) + 15) / 16 * 16;
                 bh = ((maxy - miny + 1) + 7) / 8 * 8;
                 if (bw > 128 || bh > 256 || bw * bh > static_cast<uint32_t>(kMaxBoxBytes)) box = false;
+                // The box pitch in shared memory is bw bytes.  With an even number of 16-byte columns
+                // (pitch 32/64/96/128 B) source rows one or two apart start on the same banks, and a
+                // consumer warp (4 tile rows) reads several source rows at the same x: bank conflicts.
+                // One more column (read from L2, never referenced) makes the pitch an odd multiple of
+                // 16 B, which staggers 8 consecutive rows over the banks.
+                if (box && odd_pitch && (bw / 16) % 2 == 0 && bw + 16 <= 128 && (bw + 16) * bh <= static_cast<uint32_t>(kMaxBoxBytes)) bw += 16;
             }
             // entry blocks start 16-byte aligned
             plan.entries.resize((plan.entries.size() + 15) / 16 * 16);
@@ -110,6 +117,9 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
 
 TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int threads) {
     TilePlan plan;
+    // BLINKY_BOX_PITCH=even keeps the tightest box; default: odd multiples of 16 bytes (see plan_tile_row)
+    const char *pitch_env = getenv("BLINKY_BOX_PITCH");
+    const bool odd_pitch = !(pitch_env && strcmp(pitch_env, "even") == 0);
     plan.width = width;
     plan.height = height;
     plan.platesize = platesize;
@@ -120,7 +130,7 @@ TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int plate
         TilePlan &r = rows[static_cast<size_t>(ty)];
         r.tiles_x = plan.tiles_x;
         r.tiles.reserve(static_cast<size_t>(plan.tiles_x));
-        plan_tile_row(packed, width, height, platesize, allow_box, ty, r);
+        plan_tile_row(packed, width, height, platesize, allow_box, odd_pitch, ty, r);
     });
     // stitch the rows together in order (every entry block is a multiple of 16 bytes)
     size_t total = 0;
