@@ -70,7 +70,7 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
                 // (pitch 32/64/96/128 B) source rows one or two apart start on the same banks, and a
                 // consumer warp (4 tile rows) reads several source rows at the same x: bank conflicts.
                 // One more column (read from L2, never referenced) makes the pitch an odd multiple of
-                // 16 B, which staggers 8 consecutive rows over the banks.
+                // 16 B, which staggers 8 consecutive rows over the banks.  (Optional: it did not pay.)
                 if (box && odd_pitch && (bw / 16) % 2 == 0 && bw + 16 <= 128 && (bw + 16) * bh <= static_cast<uint32_t>(kMaxBoxBytes)) bw += 16;
             }
             // entry blocks start 16-byte aligned
@@ -117,9 +117,11 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
 
 TilePlan make_tile_plan(const uint32_t *packed, int width, int height, int platesize, bool allow_box, int threads) {
     TilePlan plan;
-    // BLINKY_BOX_PITCH=even keeps the tightest box; default: odd multiples of 16 bytes (see plan_tile_row)
+    // BLINKY_BOX_PITCH=odd pads boxes to odd multiples of 16 bytes (see plan_tile_row).  Measured on
+    // B200 (scripts/pitch_ab.sh, profiles/r1e_box_pitch_ab.txt): no difference within noise on any
+    // BASELINE lens while staging 13 % more bytes, so the tightest box stays the default.
     const char *pitch_env = getenv("BLINKY_BOX_PITCH");
-    const bool odd_pitch = !(pitch_env && strcmp(pitch_env, "even") == 0);
+    const bool odd_pitch = pitch_env && strcmp(pitch_env, "odd") == 0;
     plan.width = width;
     plan.height = height;
     plan.platesize = platesize;
