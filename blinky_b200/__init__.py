@@ -60,6 +60,7 @@ _SIGNATURES = [
     ("blinky_needs_rebuild", c_int, [_CTX, c_int, c_int, c_int]),
     ("blinky_build_info", c_char_p, [_CTX]),
     ("blinky_plan_digest", ctypes.c_uint64, [_CTX, c_int]),
+    ("blinky_get_tile_plan", c_int, [_CTX, c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t)]),
     ("blinky_compile_lens", c_int, [_CTX, c_int, POINTER(c_size_t)]),
     ("blinky_fisheye_enabled", c_int, [_CTX]),
     ("blinky_lens_valid", c_int, [_CTX]),
@@ -242,6 +243,18 @@ class Fisheye:
     def build_info(self) -> str:
         """How the last lensmap was built ("device: ..." or "host ...")."""
         return self._lib.blinky_build_info(self._ctx).decode()
+
+    TILE_DTYPE = np.dtype([("entry_offset", "<u4"), ("box_x", "<i2"), ("box_y", "<i2"), ("plate", "u1"), ("type", "u1"),
+                           ("box_w16", "u1"), ("box_h8", "u1"), ("px", "<u2"), ("py", "<u2")])
+
+    def tile_plan(self) -> tuple[np.ndarray, np.ndarray]:
+        """(tile descriptors as a structured array, entry bytes) exactly as uploaded to the device"""
+        nt, nb = c_size_t(), c_size_t()
+        self._check(self._lib.blinky_get_tile_plan(self._ctx, None, 0, None, 0, ctypes.byref(nt), ctypes.byref(nb)))
+        tiles = np.zeros(nt.value, self.TILE_DTYPE)
+        entries = np.zeros(nb.value, np.uint8)
+        self._check(self._lib.blinky_get_tile_plan(self._ctx, tiles.ctypes.data, tiles.nbytes, entries.ctypes.data, entries.nbytes, None, None))
+        return tiles, entries
 
     def plan_digest(self, threads: int = 1) -> int:
         return int(self._lib.blinky_plan_digest(self._ctx, threads))

@@ -429,6 +429,24 @@ const char *blinky_plan_summary(blinky_ctx *ctx) {
     ctx->scratch = buf;
     return ctx->scratch.c_str();
 }
+int blinky_get_tile_plan(blinky_ctx *ctx, void *tiles_out, size_t tiles_cap, void *entries_out, size_t entries_cap, size_t *ntiles,
+                         size_t *entry_bytes) {
+    if (!ctx->host.built()) return set_err(ctx, BLINKY_E_STATE, "no lensmap built");
+    blinky::TilePlan pl = blinky::make_tile_plan(ctx->host.packed().data(), ctx->host.width(), ctx->host.height(),
+                                                 ctx->host.platesize(), ctx->host.platesize() % 16 == 0, ctx->host.worker_threads());
+    if (ntiles) *ntiles = pl.tiles.size();
+    if (entry_bytes) *entry_bytes = pl.entries.size();
+    if (tiles_out) {
+        if (tiles_cap < pl.tiles.size() * sizeof(blinky::TileDesc)) return set_err(ctx, BLINKY_E_INVALID, "tile buffer too small");
+        memcpy(tiles_out, pl.tiles.data(), pl.tiles.size() * sizeof(blinky::TileDesc));
+    }
+    if (entries_out) {
+        if (entries_cap < pl.entries.size()) return set_err(ctx, BLINKY_E_INVALID, "entry buffer too small");
+        memcpy(entries_out, pl.entries.data(), pl.entries.size());
+    }
+    return BLINKY_OK;
+}
+
 uint64_t blinky_plan_digest(blinky_ctx *ctx, int threads) {
     if (!ctx->host.built()) return 0;
     blinky::TilePlan pl = blinky::make_tile_plan(ctx->host.packed().data(), ctx->host.width(), ctx->host.height(),

@@ -249,6 +249,14 @@ int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_st
 /* one-line description of how the current lensmap was tiled for the TMA kernel
  * (tile counts per class, staged bytes per pixel); "" before a build */
 const char *blinky_plan_summary(blinky_ctx *ctx);
+/* The tile plan the kernels read: 16-byte tile descriptors
+ * {u32 entry_offset; i16 box_x, box_y; u8 plate, type (0 empty, 1 box, 2 gather, 3 box fully mapped),
+ * box_w/16, box_h/8; u16 px, py} with BOX tiles first, and the entry blocks (per tile 1024 entries:
+ * 16-bit {bit 15 valid, bits 12-14 tint, bits 0-11 offset inside the box} for BOX tiles, the packed
+ * 32-bit lensmap format for GATHER tiles).  Pass NULL buffers to query the sizes.  Works on CPU-only
+ * contexts; the tests interpret the plan on the CPU to pin this layout. */
+int blinky_get_tile_plan(blinky_ctx *ctx, void *tiles_out, size_t tiles_cap, void *entries_out, size_t entries_cap, size_t *ntiles,
+                         size_t *entry_bytes);
 /* FNV-1a digest of the tile table + entry blocks planned on `threads` host threads (the plan
  * must not depend on the thread count; used by the tests) */
 uint64_t blinky_plan_digest(blinky_ctx *ctx, int threads);
