@@ -59,6 +59,7 @@ struct FuncInfo {
     const Function *fn = nullptr;
     std::string cname;
     int arity = -1;
+    std::vector<int> res_types;  // per result: -1 unknown yet, else static_cast<int>(VT::Num / VT::Bool)
     bool in_progress = false;
     bool done = false;
     std::string code;
@@ -82,6 +83,8 @@ public:
             entry_fn_ = fn;
             FuncInfo &fi = gen_function(fn);
             if (fi.arity != nresults) fail(name + " must return " + (nresults == 3 ? std::string("three") : std::to_string(nresults)) + " numbers (or nil)");
+            for (int t : fi.res_types)
+                if (t == static_cast<int>(VT::Bool)) fail(name + " must return numbers, not booleans");
             std::ostringstream o;
             o << "LT_FN void lt_init_mut(Ctx &c) {\n    (void)c;\n";
             for (size_t i = 0; i < mutable_init_.size(); ++i) o << "    c.mg[" << i << "] = LtD(" << num_literal(mutable_init_[i]) << ");\n";
@@ -728,9 +731,24 @@ private:
             EOut o;
             o.code = t + "[" + std::to_string(i) + "]";
             o.tainted = true;
+            if (static_cast<size_t>(i) < fi.res_types.size() && fi.res_types[static_cast<size_t>(i)] == static_cast<int>(VT::Bool)) {
+                o.code = "(" + o.code + ".v != 0.0)";
+                o.type = VT::Bool;
+                o.tainted = false;
+            }
             res.push_back(o);
         }
         return res;
+    }
+
+    // results travel as LtD; a boolean result is 1.0 / 0.0 (exact) and is decoded at the call site
+    std::string encode_result(Gen &g, size_t i, const EOut &v, int line_no) {
+        if (v.type == VT::Arr) fail("arrays cannot be returned", line_no);
+        if (g.fi->res_types.size() <= i) g.fi->res_types.resize(i + 1, -1);
+        int &t = g.fi->res_types[i];
+        if (t == -1) t = static_cast<int>(v.type);
+        else if (t != static_cast<int>(v.type)) fail("a function returns a number on one path and a boolean on another", line_no);
+        return v.type == VT::Bool ? "LtD(" + v.code + " ? 1.0 : 0.0)" : v.code;
     }
 
     // ------------------------------------------------------------------ statements
@@ -905,7 +923,8 @@ private:
                 if (s->exprs.size() == 1 && s->exprs[0]->k == EK::Call) {
                     std::vector<EOut> vals = gen_call(g, s->exprs[0], -2);
                     if (static_cast<int>(vals.size()) < K) fail("a function returns a different number of values on different paths", s->line);
-                    for (int i = 0; i < K; ++i) line(g, "r[" + std::to_string(i) + "] = " + vals[static_cast<size_t>(i)].code + ";");
+                    for (int i = 0; i < K; ++i)
+                        line(g, "r[" + std::to_string(i) + "] = " + encode_result(g, static_cast<size_t>(i), vals[static_cast<size_t>(i)], s->line) + ";");
                     line(g, "return true;");
                     return;
                 }
@@ -913,9 +932,8 @@ private:
                 if (static_cast<int>(vals.size()) != K) fail("a function returns a different number of values on different paths", s->line);
                 std::vector<std::string> tmps;
                 for (int i = 0; i < K; ++i) {
-                    if (vals[static_cast<size_t>(i)].type != VT::Num) fail("only numbers can be returned", s->line);
                     std::string t = new_tmp(g, "re");
-                    line(g, "const LtD " + t + " = " + vals[static_cast<size_t>(i)].code + ";");
+                    line(g, "const LtD " + t + " = " + encode_result(g, static_cast<size_t>(i), vals[static_cast<size_t>(i)], s->line) + ";");
                     tmps.push_back(t);
                 }
                 for (int i = 0; i < K; ++i) line(g, "r[" + std::to_string(i) + "] = " + tmps[static_cast<size_t>(i)] + ";");

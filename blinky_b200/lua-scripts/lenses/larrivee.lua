@@ -1,13 +1,17 @@
--- Larrivee projection (forward map only).
-max_fov = 360
-max_vfov = 180
-lens_width = 2*pi
-lens_height = pi/2 / cos(pi/2/2) * 2
+-- Larrivee (1988), a compromise world map with bulging polar regions.  Forward map only.
+--
+--   x = lon (1 + sqrt(cos lat)) / 2
+--   y = lat / (cos(lat/2) cos(lon/6))
 onload = "f_contain"
+max_vfov = 180
+max_fov = 360
+lens_height = pi/2 / cos(pi/2/2) * 2   -- y at the pole on the central meridian, doubled
+lens_width = 2*pi
 
-function lens_forward(x, y, z)
-  local lat, lon = ray_to_latlon(x, y, z)
-  local px = (0.5 + 0.5*sqrt(cos(lat)))*lon
-  local py = lat / (cos(lat/2)*cos(lon/6))
-  return px, py
+local function project(lat, lon)
+  return (0.5 + 0.5*sqrt(cos(lat)))*lon, lat / (cos(lat/2)*cos(lon/6))
+end
+
+function lens_forward(rx, ry, rz)
+  return project(ray_to_latlon(rx, ry, rz))
 end

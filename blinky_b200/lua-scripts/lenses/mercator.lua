@@ -1,19 +1,19 @@
--- Mercator: y = ln tan(pi/4 + latitude/2).
-max_fov = 360
-max_vfov = 180
-lens_width = 2*pi
+-- Mercator: the conformal cylinder.  x = longitude, y = ln tan(pi/4 + lat/2), whose
+-- inverse is the Gudermannian lat = atan(sinh y).  Endless towards the poles: only a
+-- width is declared and the default zoom covers the screen.
 onload = "f_cover"
+lens_width = 2*pi
+max_vfov = 180
+max_fov = 360
+
+local function gudermannian(y) return atan(sinh(y)) end
 
 function lens_inverse(x, y)
-  if abs(x) > pi then
-    return nil
-  end
-  local lon = x
-  local lat = atan(sinh(y))
-  return latlon_to_ray(lat, lon)
+  if abs(x) > pi then return nil end   -- one turn around the cylinder
+  return latlon_to_ray(gudermannian(y), x)
 end
 
-function lens_forward(x, y, z)
-  local lat, lon = ray_to_latlon(x, y, z)
+function lens_forward(rx, ry, rz)
+  local lat, lon = ray_to_latlon(rx, ry, rz)
   return lon, log(tan(pi*0.25+lat*0.5))
 end

@@ -1,22 +1,20 @@
--- Miller cylindrical: Mercator with latitude scaled by 4/5.
-local top = 1.25*log(tan(0.25*pi+0.4*pi*0.5))
-
-max_fov = 360
-max_vfov = 180
-lens_width = 2*pi
-lens_height = top*2
+-- Miller cylindrical: Mercator applied to 4/5 of the latitude and stretched back by 5/4,
+-- which keeps the poles on the map:  y = 5/4 ln tan(pi/4 + 2/5 lat).
 onload = "f_contain"
+max_vfov = 180
+max_fov = 360
+
+local top = 1.25*log(tan(0.25*pi+0.4*pi*0.5))   -- y of the pole
+lens_height = top*2
+lens_width = 2*pi
 
 function lens_inverse(x, y)
-  if abs(y) > top or abs(x) > pi then
-    return nil
-  end
-  local lon = x
-  local lat = 5/4*atan(sinh(4/5*y))
-  return latlon_to_ray(lat, lon)
+  local off_map = abs(y) > top or abs(x) > pi
+  if off_map then return nil end
+  return latlon_to_ray(5/4*atan(sinh(4/5*y)), x)
 end
 
-function lens_forward(x, y, z)
-  local lat, lon = ray_to_latlon(x, y, z)
+function lens_forward(rx, ry, rz)
+  local lat, lon = ray_to_latlon(rx, ry, rz)
   return lon, 1.25*log(tan(0.25*pi+0.4*lat))
 end

@@ -1,14 +1,17 @@
--- American polyconic projection (forward map only).
-max_fov = 360
-max_vfov = 180
+-- American polyconic: every parallel is the arc it would be on its own tangent cone.
+-- Forward map only; no natural frame, so it opens at a 360 degree fit.
+--
+--   E = lon sin lat,   x = cot lat sin E,   y = lat + cot lat (1 - cos E)
+--   (on the equator the cones degenerate: x = lon, y = 0)
 onload = "f_fov 360"
+max_vfov = 180
+max_fov = 360
 
-function lens_forward(x, y, z)
-  local lat, lon = ray_to_latlon(x, y, z)
-  if lat == 0 then
-    return lon, 0
-  end
-  local px = 1/tan(lat)*sin(lon*sin(lat))
-  local py = lat + 1/tan(lat)*(1 - cos(lon*sin(lat)))
-  return px, py
+local function project(lat, lon)
+  if lat == 0 then return lon, 0 end
+  return 1/tan(lat)*sin(lon*sin(lat)), lat + 1/tan(lat)*(1 - cos(lon*sin(lat)))
+end
+
+function lens_forward(rx, ry, rz)
+  return project(ray_to_latlon(rx, ry, rz))
 end

@@ -1,7 +1,8 @@
--- Rectilinear (ordinary perspective): r = tan(theta).
-max_fov = 180
-max_vfov = 180
+-- Rectilinear: the ordinary pinhole camera, r = tan(theta).  Straight lines stay
+-- straight, which is exactly why it cannot reach 180 degrees.
 onload = "f_fov 110"
+max_vfov = 180
+max_fov = 180
 
 function lens_inverse(x, y)
   local r = sqrt(x*x+y*y)
@@ -10,9 +11,7 @@ function lens_inverse(x, y)
   return x/r*s, y/r*s, cos(theta)
 end
 
-function lens_forward(x, y, z)
-  local theta = acos(z)
-  local r = tan(theta)
-  local c = r/sqrt(x*x+y*y)
-  return x*c, y*c
+function lens_forward(rx, ry, rz)
+  local k = tan(acos(rz))/sqrt(rx*rx+ry*ry)
+  return rx*k, ry*k
 end

@@ -1,11 +1,13 @@
--- Sinusoidal equal-area projection (forward map only)
-max_fov = 360
-max_vfov = 180
-lens_width = 2*pi
-lens_height = pi
+-- Sinusoidal (Sanson-Flamsteed) equal-area map: parallels keep their true length,
+-- x = lon cos lat, y = lat.  Forward map only.
 onload = "f_contain"
+lens_height = pi
+lens_width = 2*pi
+max_vfov = 180
+max_fov = 360
 
-function lens_forward(x, y, z)
-  local lat, lon = ray_to_latlon(x, y, z)
-  return lon*cos(lat), lat
+local function project(lat, lon) return lon*cos(lat), lat end
+
+function lens_forward(rx, ry, rz)
+  return project(ray_to_latlon(rx, ry, rz))
 end

@@ -29,54 +29,54 @@ local cut_y = lens_height/2*0.81
 local eps = 0.0001
 local halfpi = pi/2
 
-function lens_inverse(x, y)
-  if abs(y) >= lens_height/2 then
-    return nil
+-- Newton-Raphson on the forward equations in (lambda, phi), started at (x, y):
+--   F(lambda, phi) = forward(lambda, phi) - (x, y) = 0
+-- with the analytic Jacobian (Ipbuker & Bildirici, "A General Algorithm for the Inverse
+-- Transformation of Map Projections Using Jacobian Matrices", 2002).
+local function newton_step(lambda, phi, x, y)
+  local cp = cos(phi)
+  local sp = sin(phi)
+  local s2p = sin(2 * phi)
+  local sp_sq = sp * sp
+  local cp_sq = cp * cp
+  local sl = sin(lambda)
+  local ch = cos(lambda / 2)
+  local sh = sin(lambda / 2)
+  local sh_sq = sh * sh
+  local gap = 1 - cp_sq * ch * ch          -- 1 - cos^2(angular distance to the centre)
+  local arc, inv                           -- distance / sin(distance), 1 / sin^2(distance)
+  if gap ~= 0 then
+    inv = 1/gap
+    arc = acos(cp * ch) * sqrt(inv)
+  else
+    arc = 0
+    inv = 0
   end
-  if abs(x) > cut_x and abs(y) > cut_y then
-    return nil
-  end
+  local fx = .5 * (2 * arc * cp * sh + lambda / halfpi) - x
+  local fy = .5 * (arc * sp + phi) - y
+  local x_l = .5 * inv * (cp_sq * sh_sq + arc * cp * ch * sp_sq) + .5 / halfpi
+  local x_p = inv * (sl * s2p / 4 - arc * sp * sh)
+  local y_l = .125 * inv * (s2p * sh - arc * sp * cp_sq * sl)
+  local y_p = .5 * inv * (sp_sq * ch + arc * sh_sq * cp) + .5
+  local det = x_p * y_l - y_p * x_l
+  return (fy * x_p - fx * y_p) / det, (fx * y_l - fy * x_l) / det
+end
 
-  local lambda = x
-  local phi = y
-  for iter = 1, 25 do
-    local cosphi = cos(phi)
-    local sinphi = sin(phi)
-    local sin_2phi = sin(2 * phi)
-    local sin2phi = sinphi * sinphi
-    local cos2phi = cosphi * cosphi
-    local sinlambda = sin(lambda)
-    local coslambda_2 = cos(lambda / 2)
-    local sinlambda_2 = sin(lambda / 2)
-    local sin2lambda_2 = sinlambda_2 * sinlambda_2
-    local C = 1 - cos2phi * coslambda_2 * coslambda_2
-    local E, F
-    if C ~= 0 then
-      F = 1/C
-      E = acos(cosphi * coslambda_2) * sqrt(F)
-    else
-      E = 0
-      F = 0
-    end
-    local fx = .5 * (2 * E * cosphi * sinlambda_2 + lambda / halfpi) - x
-    local fy = .5 * (E * sinphi + phi) - y
-    local dxdl = .5 * F * (cos2phi * sin2lambda_2 + E * cosphi * coslambda_2 * sin2phi) + .5 / halfpi
-    local dxdp = F * (sinlambda * sin_2phi / 4 - E * sinphi * sinlambda_2)
-    local dydl = .125 * F * (sin_2phi * sinlambda_2 - E * sinphi * cos2phi * sinlambda)
-    local dydp = .5 * F * (sin2phi * coslambda_2 + E * sin2lambda_2 * cosphi) + .5
-    local den = dxdp * dydl - dydp * dxdl
-    local dl = (fy * dxdp - fx * dydp) / den
-    local dp = (fx * dydl - fy * dxdl) / den
+function lens_inverse(x, y)
+  if abs(y) >= lens_height/2 then return nil end
+  if abs(x) > cut_x and abs(y) > cut_y then return nil end
+
+  local lambda, phi = x, y
+  for _ = 1, 25 do
+    local dl, dp = newton_step(lambda, phi, x, y)
     lambda = lambda - dl
     phi = phi - dp
-    if abs(dl) < eps and abs(dp) < eps then
-      break
-    end
+    if abs(dl) < eps and abs(dp) < eps then break end
   end
 
   -- keep only points inside the outline at this latitude
-  local x0 = lens_forward(latlon_to_ray(phi, pi))
-  if abs(x) < abs(x0) then
+  local outline = lens_forward(latlon_to_ray(phi, pi))
+  if abs(x) < abs(outline) then
     return latlon_to_ray(phi, lambda)
   end
   return nil

@@ -24,6 +24,7 @@ class Gen:
         self.nvars = 0
         self.indent = 1
         self.helpers = []  # (name, nargs, nres)
+        self.predicates = []  # (name, nargs): helper functions returning a boolean
         self.arrays = []   # (name, size)
 
     def emit(self, s):
@@ -71,6 +72,9 @@ class Gen:
             return f"({self.cond(names, depth + 1)} {j} {self.cond(names, depth + 1)})"
         if depth < 2 and r.random() < 0.15:
             return f"not ({self.cond(names, depth + 1)})"
+        if self.predicates and r.random() < 0.2:
+            name, nargs = r.choice(self.predicates)
+            return f"{name}({', '.join(self.expr(names, 2) for _ in range(nargs))})"
         return f"{self.expr(names, 2)} {r.choice(['<', '<=', '>', '>=', '==', '~='])} {self.expr(names, 2)}"
 
     def new_var(self):
@@ -168,6 +172,10 @@ class Gen:
             self.arrays = saved_arrays
             head += [f"local function h{h}({', '.join(args)})"] + self.lines + ["end"]
             self.helpers.append((f"h{h}", nargs, nres))
+        if r.random() < 0.5:  # a predicate: helper returning a boolean
+            args = ["a0", "a1"][: r.randint(1, 2)]
+            head += [f"local function pred0({', '.join(args)})", f"  return {self.cond(args)}", "end"]
+            self.predicates.append(("pred0", len(args)))
         self.lines, self.indent = [], 1
         if forward:  # lens_forward(x, y, z) -> x, y
             names = self.block(["x", "y", "z"], 0, 6)
