@@ -847,7 +847,9 @@ bool FisheyeHost::lens_device_source(bool cuda, std::string *source, std::string
         *why = r.error;
         return false;
     }
-    *source = transpile_prelude(cuda) + r.source;
+    // BLINKY_LENS_NOINLINE=1: script functions become real device calls (faster NVRTC, slower kernel)
+    const char *ni = getenv("BLINKY_LENS_NOINLINE");
+    *source = transpile_prelude(cuda, ni && ni[0] == '1') + r.source;
     return true;
 }
 

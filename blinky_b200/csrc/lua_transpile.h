@@ -45,6 +45,6 @@ TranspileResult transpile_lens(minilua::State &L, const minilua::Value &lens_inv
 TranspileResult transpile_lens_forward(minilua::State &L, const minilua::Value &lens_forward);
 
 // Support code the generated source needs.  cuda = true: __device__ functions; false: plain C++.
-std::string transpile_prelude(bool cuda);
+std::string transpile_prelude(bool cuda, bool noinline_user_functions = false);
 
 }  // namespace blinky
