@@ -77,3 +77,20 @@ def test_error_codes_and_messages(bb, host):
     with pytest.raises(bb.BlinkyError):
         host.lensmap_packed() if False else host.set_zoom(99)
     assert bb.load_library().blinky_version().startswith(b"blinky_b200")
+
+
+def test_c_example_builds_links_and_refuses_to_warp_without_a_gpu(bb, tmp_path):
+    """examples/headless_warp.c against include/blinky_b200.h + the in-tree .so, as a C host would"""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "headless_warp")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "headless_warp.c"),
+                        "-L", os.path.dirname(bb.LIB_PATH), "-lblinky_b200", "-Wl,-rpath," + os.path.dirname(bb.LIB_PATH), "-o", exe],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[:2000]
+    r = subprocess.run([exe, "-1", "hammer", "320", "200", "96", "2"], capture_output=True, text=True, cwd=root)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)  # BLINKY_E_NODEVICE path
+    assert "40176 mapped pixels" in r.stdout and "f_lens hammer; f_contain" in r.stdout
+    assert "no CPU fallback" in r.stderr
