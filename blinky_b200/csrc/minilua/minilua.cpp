@@ -10,6 +10,7 @@
 
 #include <cerrno>
 #include <cinttypes>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -2205,6 +2206,39 @@ void t_concat(State &L, const Value *a, int n, ValueList &out, void *) {
     }
     out.push_back(L.new_string(s));
 }
+// table.sort (ltablib.c sort): ascending by `<` on numbers / strings, or by the caller's order
+// function.  A merge sort: an inconsistent order function gives some permutation, never a crash.
+bool sort_less(State &L, const Value &cmp, const Value &x, const Value &y) {
+    if (cmp.is_function()) {
+        Value args[2] = {x, y};
+        ValueList r;
+        L.call(cmp, args, 2, r);
+        return r.size() > 0 && r[0].truthy();
+    }
+    if (x.is_number() && y.is_number()) return x.num() < y.num();
+    if (x.is_string() && y.is_string()) return x.str() < y.str();
+    throw LuaError(std::string("attempt to compare ") + State::type_name(x) + " with " + State::type_name(y));
+}
+void t_sort(State &L, const Value *a, int n, ValueList &, void *) {
+    Table *t = check_table(a, n, 1, "sort");
+    Value cmp = n >= 2 ? a[1] : Value();
+    if (!cmp.is_nil() && !cmp.is_function()) arg_error(2, "sort", "function expected");
+    const int64_t size = t->length();
+    std::vector<Value> v, tmp;
+    for (int64_t i = 1; i <= size; ++i) v.push_back(t->get_int(i));
+    tmp.resize(v.size());
+    for (size_t width = 1; width < v.size(); width *= 2) {
+        for (size_t lo = 0; lo < v.size(); lo += 2 * width) {
+            const size_t mid = std::min(lo + width, v.size()), hi = std::min(lo + 2 * width, v.size());
+            size_t i = lo, j = mid, k = lo;
+            while (i < mid && j < hi) tmp[k++] = sort_less(L, cmp, v[j], v[i]) ? v[j++] : v[i++];
+            while (i < mid) tmp[k++] = v[i++];
+            while (j < hi) tmp[k++] = v[j++];
+        }
+        v.swap(tmp);
+    }
+    for (int64_t i = 1; i <= size; ++i) t->set_int(i, v[static_cast<size_t>(i - 1)]);
+}
 void t_pack(State &L, const Value *a, int n, ValueList &out, void *) {
     Value tv = L.new_table();
     Table *t = static_cast<Table *>(tv.obj());
@@ -2677,6 +2711,7 @@ void State::open_libs() {
     reg(*this, t, "insert", t_insert);
     reg(*this, t, "remove", t_remove);
     reg(*this, t, "concat", t_concat);
+    reg(*this, t, "sort", t_sort);
     reg(*this, t, "pack", t_pack);
     set_global("table", tv);
     set_global("unpack", t->get(new_string("unpack")));  // 5.1 alias, harmless

@@ -212,3 +212,19 @@ for i = 1, 300000 do
 end
 print("done")
 """, "done\n")
+
+
+def test_table_sort(lua):
+    ok(lua, """
+local t = {3,1,2,9,-4,7.5}
+table.sort(t); print(table.concat(t, ","))
+table.sort(t, function(a,b) return a > b end); print(table.concat(t, ","))
+local w = {"pear","apple","fig"}; table.sort(w); print(table.concat(w, " "))
+print(pcall(table.sort, {1,"x"}))
+local big = {}
+for i = 1, 1000 do big[i] = (i * 7919) % 1013 end
+table.sort(big)
+local sorted = true
+for i = 2, #big do if big[i-1] > big[i] then sorted = false end end
+print(sorted, #big)
+""", "-4,1,2,3,7.5,9\n9,7.5,3,2,1,-4\napple fig pear\nfalse\tattempt to compare string with number\ntrue\t1000\n")
