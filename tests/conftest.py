@@ -60,12 +60,23 @@ def script_dir(bb):
     return bb.SCRIPT_DIR
 
 
+def _gpu_run(config) -> bool:
+    """True when this is the GPU suite (`-m gpu`): there a missing checker is a failure, not a skip"""
+    expr = (config.getoption("markexpr", "") or "").replace(" ", "")
+    return "gpu" in expr and "notgpu" not in expr
+
+
 @pytest.fixture(scope="session")
-def ref(bb, palette, script_dir):
-    """the compiled UNMODIFIED reference (oracle/_ref); skipped where it was never built"""
+def ref(request, bb, palette, script_dir):
+    """the compiled UNMODIFIED reference (oracle/_ref).  Built here from /root/reference and shipped to
+    the GPU box with the snapshot: the GPU suite FAILS without it (a skip would read as green); only a
+    CPU run on a box that never had the reference tree may skip."""
     from oracle.pyoracle import RefOracle
 
     if not RefOracle.available():
+        if _gpu_run(request.config):
+            pytest.fail("oracle/_ref/libblinky_ref.so is missing on the GPU box: run __graft_entry__.build() where "
+                        "/root/reference exists (the built .so travels with the gpurun snapshot)")
         pytest.skip("oracle/_ref/libblinky_ref.so not built (needs /root/reference at build time)")
     return RefOracle.get(script_dir, palette)
 
@@ -79,10 +90,12 @@ def host(bb, palette):
 
 
 @pytest.fixture(scope="session")
-def cuda_device():
+def cuda_device(request):
     import torch
 
     if not torch.cuda.is_available():
+        if _gpu_run(request.config):
+            pytest.fail("-m gpu was asked for but torch sees no CUDA device")
         pytest.skip("no CUDA device")
     return 0
 

@@ -16,13 +16,62 @@ def fe(bb, palette, cuda_device):
     f.close()
 
 
+# every BASELINE.json configuration at its full size (C2, C3, the five C4 lenses, both C5 globes)
 CONFIGS = [
     ("C2", 1920, 1080, 1024, "cube", "panini", "f_fov 170", False),
     ("C3", 3840, 2160, 2048, "cube", "quincuncial", "f_cover", True),
     ("C4-panini", 3840, 2160, 2048, "cube", "panini", "f_fov 180", False),
+    ("C4-stereographic/C5-cube", 3840, 2160, 2048, "cube", "stereographic", "f_fov 180", False),
+    ("C4-equirect", 3840, 2160, 2048, "cube", "equirect", "f_contain", False),
+    ("C4-hammer", 3840, 2160, 2048, "cube", "hammer", "f_contain", False),
     ("C4-fisheye1", 3840, 2160, 2048, "cube", "fisheye1", "f_contain", False),
     ("C5-trism", 3840, 2160, 2048, "trism", "stereographic", "f_fov 180", False),
 ]
+
+
+def _setup(fe, globe, lens, zoom, rubix):
+    fe.command(f"f_globe {globe}")
+    fe.command(f"f_lens {lens}")
+    fe.command(zoom)
+    fe.set_rubix(rubix)
+
+
+@pytest.mark.parametrize("name,W,H,PS,globe,lens,zoom,rubix", CONFIGS)
+def test_full_size_device_built_map(bb, fe, restate, palette, name, W, H, PS, globe, lens, zoom, rubix):
+    """The path bench.py times: lensmap built on the GPU (threads=0: translated lens + NVRTC), then the
+    default kernels.  The map must equal the oracle's (C transcription, engine/NQ/fisheye.c:2084-2124)
+    and the warped frames must equal the oracle's render (:2406-2424), bit for bit."""
+    import torch
+
+    _setup(fe, globe, lens, zoom, rubix)
+    fe.build_lensmap(W, H, PS, threads=0)
+    assert fe.build_info.startswith("device"), fe.build_info
+    z = zoom.split()
+    om = restate.build(globe, lens, W, H, PS, zoom=(z[0], int(z[1]) if len(z) > 1 else 0))
+    idx, tint = fe.lensmap()
+    assert np.array_equal(idx, om["idx"]) and np.array_equal(tint, om["tint"])
+    assert fe.display() == om["display"] and fe.scale == om["scale"]
+    P = fe.numplates
+    bg = bb.synthetic_background(W, H)
+    fe.set_background(bg)
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    d_faces = torch.randint(0, 256, (3, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+    faces = d_faces.cpu().numpy()
+    pm = restate.palmaps(palette)
+    d_out = torch.zeros((3, H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(d_faces, d_out, nframes=3)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for f in range(3):
+        want = restate.render(om["idx"], om["tint"], faces[f], pm, rubix, background=bg, threads=bb.usable_cpus())
+        assert np.array_equal(got[f], want), (name, f, fe.last_kernel)
+    # single-frame launch (the in-engine shape) and the end-to-end host path on the same map
+    d_one = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    fe.warp(d_faces[1:], d_one, nframes=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_one.cpu().numpy(), got[1])
+    host = fe.warp_host(faces[2].reshape(1, -1))
+    assert np.array_equal(host[0], got[2])
 
 
 @pytest.mark.parametrize("name,W,H,PS,globe,lens,zoom,rubix", CONFIGS)
@@ -30,10 +79,7 @@ def test_full_size_parity_and_properties(bb, fe, restate, palette, name, W, H, P
     import torch
 
     threads = bb.usable_cpus()
-    fe.command(f"f_globe {globe}")
-    fe.command(f"f_lens {lens}")
-    fe.command(zoom)
-    fe.set_rubix(rubix)
+    _setup(fe, globe, lens, zoom, rubix)
     fe.build_lensmap(W, H, PS, threads)
     z = zoom.split()
     om = restate.build(globe, lens, W, H, PS, zoom=(z[0], int(z[1]) if len(z) > 1 else 0))
