@@ -112,6 +112,13 @@ _SIGNATURES = [
     ("blinky_plan_summary", c_char_p, [_CTX]),
     ("blinky_launch_count", c_int64, [_CTX]),
     ("blinky_last_kernel", c_char_p, [_CTX]),
+    ("blinky_shard_range", c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    ("blinky_shard_unique_id", c_int, [c_void_p]),
+    ("blinky_shard_init", c_int, [_CTX, c_int, c_int, c_void_p]),
+    ("blinky_shard_buffer", c_int, [_CTX, c_int, POINTER(c_void_p)]),
+    ("blinky_shard_warp_gather", c_int, [_CTX, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    ("blinky_shard_sync", c_int, [_CTX]),
+    ("blinky_shard_close", c_int, [_CTX]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -441,12 +448,56 @@ class Fisheye:
     def ipc_close(self, ptr: int):
         self._check(self._lib.blinky_ipc_close(self._ctx, ptr))
 
+    # -- sharded batches (one process per GPU) ----------------------------------------------
+    def shard_init(self, rank: int, world: int, unique_id: bytes):
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        self._check(self._lib.blinky_shard_init(self._ctx, rank, world, ctypes.addressof(buf)))
+
+    def shard_buffer(self, total_frames: int) -> int | None:
+        """collective; rank 0 gets the device address of the gather buffer, the others None"""
+        p = c_void_p()
+        self._check(self._lib.blinky_shard_buffer(self._ctx, total_frames, ctypes.byref(p)))
+        return p.value
+
+    def shard_warp_gather(self, d_faces, total_frames: int, mode: int = 0, chunk_frames: int = 2, face_stride: int | None = None,
+                          stream: int | None = None):
+        if face_stride is None:
+            face_stride = self.numplates * self.platesize * self.platesize
+        self._check(self._lib.blinky_shard_warp_gather(self._ctx, _ptr(d_faces), face_stride, total_frames, mode, chunk_frames, stream))
+
+    def shard_sync(self):
+        self._check(self._lib.blinky_shard_sync(self._ctx))
+
+    def shard_close(self):
+        self._check(self._lib.blinky_shard_close(self._ctx))
+
     def set_rgba_table(self, table: np.ndarray):
         t = np.ascontiguousarray(table, dtype=np.uint32).reshape(256)
         self._check(self._lib.blinky_set_rgba_table(self._ctx, t.ctypes.data))
 
     def sync(self):
         self._check(self._lib.blinky_sync(self._ctx))
+
+
+GATHER_NCCL, GATHER_PEER_COPY, GATHER_PEER_STORE = 0, 1, 2
+
+
+def shard_range(total_frames: int, rank: int, world: int) -> range:
+    """frames owned by `rank` (blinky_shard_range: contiguous blocks, sizes differ by at most one)"""
+    first, count = c_int(), c_int()
+    rc = load_library().blinky_shard_range(total_frames, rank, world, ctypes.byref(first), ctypes.byref(count))
+    if rc != OK:
+        raise BlinkyError(rc, "blinky_shard_range: bad arguments")
+    return range(first.value, first.value + count.value)
+
+
+def shard_unique_id() -> bytes:
+    """128-byte NCCL id made on one rank and carried to the others by the caller"""
+    buf = ctypes.create_string_buffer(128)
+    rc = load_library().blinky_shard_unique_id(ctypes.addressof(buf))
+    if rc != OK:
+        raise BlinkyError(rc, "blinky_shard_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 def usable_cpus() -> int:

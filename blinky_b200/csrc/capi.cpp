@@ -16,6 +16,7 @@
 
 #include "fisheye_host.h"
 #include "lens_device.h"
+#include "shard.h"
 #include "tile_plan.h"
 #include "warp_device.h"
 
@@ -26,6 +27,7 @@ using blinky::WarpDevice;
 
 struct blinky_ctx {
     FisheyeHost host;
+    std::unique_ptr<blinky::ShardGroup> shard;  // destroyed before the device it borrows
     std::unique_ptr<WarpDevice> dev;
     std::unique_ptr<LensDevice> lens_dev;
     std::string build_info;
@@ -333,6 +335,8 @@ int blinky_save_globe(blinky_ctx *ctx, const uint8_t *faces_host, const char *di
 
 int blinky_set_kernel(blinky_ctx *ctx, int variant) {
     NEED_DEVICE(ctx);
+    if (variant != BLINKY_KERNEL_AUTO && variant != BLINKY_KERNEL_GATHER && variant != BLINKY_KERNEL_TMA)
+        return set_err(ctx, BLINKY_E_INVALID, "blinky_set_kernel: unknown kernel variant");
     ctx->dev->set_kernel(variant);
     return BLINKY_OK;
 }
@@ -461,5 +465,61 @@ uint64_t blinky_plan_digest(blinky_ctx *ctx, int threads) {
     return h;
 }
 const char *blinky_last_kernel(blinky_ctx *ctx) { return ctx->dev ? ctx->dev->last_kernel().c_str() : ""; }
+
+// ---- sharded batches ---------------------------------------------------------------------
+int blinky_shard_range(int total_frames, int rank, int world, int *first, int *count) {
+    if (world < 1 || rank < 0 || rank >= world || total_frames < 0) return BLINKY_E_INVALID;
+    blinky::shard_range(total_frames, rank, world, first, count);
+    return BLINKY_OK;
+}
+
+int blinky_shard_unique_id(unsigned char id[128]) {
+    std::string err;
+    if (!id) return BLINKY_E_INVALID;
+    if (!blinky::ShardGroup::unique_id(id, err)) {
+        fprintf(stderr, "blinky_shard_unique_id: %s\n", err.c_str());
+        return BLINKY_E_CUDA;
+    }
+    return BLINKY_OK;
+}
+
+int blinky_shard_init(blinky_ctx *ctx, int rank, int world, const unsigned char id[128]) {
+    NEED_DEVICE(ctx);
+    if (!id) return set_err(ctx, BLINKY_E_INVALID, "blinky_shard_init: id is NULL");
+    if (ctx->shard) return set_err(ctx, BLINKY_E_STATE, "blinky_shard_init: already initialised (blinky_shard_close first)");
+    std::unique_ptr<blinky::ShardGroup> g(new blinky::ShardGroup(ctx->dev.get(), ctx->dev->device()));
+    if (!g->init(rank, world, id)) return set_err(ctx, BLINKY_E_CUDA, g->last_error());
+    ctx->shard = std::move(g);
+    return BLINKY_OK;
+}
+
+int blinky_shard_buffer(blinky_ctx *ctx, int total_frames, void **root_buffer) {
+    NEED_DEVICE(ctx);
+    if (!ctx->shard) return set_err(ctx, BLINKY_E_STATE, "blinky_shard_buffer: call blinky_shard_init first");
+    if (!ctx->host.built()) return set_err(ctx, BLINKY_E_STATE, "blinky_shard_buffer: build a lensmap first (the frames have the view's size)");
+    if (total_frames < 0) return set_err(ctx, BLINKY_E_INVALID, "blinky_shard_buffer: total_frames < 0");
+    const size_t fb = static_cast<size_t>(ctx->host.width()) * ctx->host.height();
+    return ctx->shard->buffer(total_frames, fb, root_buffer) ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->shard->last_error());
+}
+
+int blinky_shard_warp_gather(blinky_ctx *ctx, const void *d_faces, size_t face_stride, int total_frames, int mode, int chunk_frames,
+                             void *stream) {
+    NEED_DEVICE(ctx);
+    if (!ctx->shard) return set_err(ctx, BLINKY_E_STATE, "blinky_shard_warp_gather: call blinky_shard_init first");
+    return ctx->shard->warp_gather(d_faces, face_stride, total_frames, mode, chunk_frames, stream)
+               ? BLINKY_OK
+               : set_err(ctx, BLINKY_E_CUDA, ctx->shard->last_error());
+}
+
+int blinky_shard_sync(blinky_ctx *ctx) {
+    NEED_DEVICE(ctx);
+    if (!ctx->shard) return set_err(ctx, BLINKY_E_STATE, "blinky_shard_sync: no shard group");
+    return ctx->shard->sync() ? BLINKY_OK : set_err(ctx, BLINKY_E_CUDA, ctx->shard->last_error());
+}
+
+int blinky_shard_close(blinky_ctx *ctx) {
+    ctx->shard.reset();
+    return BLINKY_OK;
+}
 
 }  // extern "C"

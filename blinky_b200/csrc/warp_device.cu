@@ -166,32 +166,31 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 
 
 // --------------------------------------------------------------------------
-// K2: tiled, warp-specialised kernel with TMA-staged source boxes.
-//
-// Persistent CTAs (1 producer warp + 8 consumer warps) walk work items
-// (tile, frame) in tile-major order through a kStages-deep shared-memory ring.
-//   producer (one lane): waits for a free stage, copies the 16-byte TileDesc into
-//     the stage, and issues (a) one 4-D TMA tensor load (x, y, plate, frame) of the
-//     tile's source box and (b) one bulk copy of the tile's entry block — both
-//     complete on the stage's `full` mbarrier.  It runs up to kStages items ahead,
-//     so every global-memory latency is off the consumers' critical path.
-//   consumers (256 threads, one 4-pixel quad each): wait on `full`, read the
-//     descriptor, their four entries and the four source bytes from SHARED memory,
-//     apply the tint LUT, write one 32-bit word (one 128-bit word in RGBA mode),
-//     then release the stage on its `empty` mbarrier.  No block-wide barrier.
-// GATHER tiles (plate seams, singular points) carry 32-bit entries and read the
-// globe directly, with the same 2-D thread layout (a warp covers 32x4 pixels).
+// K2: ring kernel.  Every WARP is its own pipeline (one warp per CTA, as many CTAs per SM as
+// shared memory allows): it draws work units (tile, chunk of frames) from a ticket counter,
+// keeps the tile's lensmap entries in REGISTERS for all frames of the unit, and feeds itself
+// through a private ring of TMA tensor loads:
+//   * per unit: 4 coalesced 128-bit loads give the lane its 32 16-bit entries (prefetched one
+//     unit ahead); they are unpacked once into 32 shared-memory offsets.
+//   * per frame: lane 0 has issued ONE 4-D TMA tensor load (x, y, plate, frame) of the tile's
+//     source box into a ring stage, completing on the stage's mbarrier; the warp waits, does
+//     32 byte loads from shared memory per lane (one per output pixel), packs them with PRMT
+//     into eight 32-bit words and writes them with streaming stores; the stage is refilled with
+//     the next box of the warp's sequence (this unit's later frames, then the next unit's first
+//     frames) as soon as its data sits in registers.
+// There is no producer warp, no cross-warp barrier and no per-pixel entry traffic per frame:
+// round 1's kernel was bound by the serial per-item work of its producer thread (5.2 us/frame
+// with every load and store removed, profiles/r2_c1_k2lab.txt).
+// GATHER tiles (plate seams, singular points, boxes too large to stage) carry 32-bit entries and
+// read the globe directly: lane = column, so one warp-level load covers 32 consecutive screen
+// pixels of one row.  EMPTY tiles copy the background.
 // --------------------------------------------------------------------------
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 4;
-constexpr int kConsumerThreads = kConsumerWarps * 32;   // 128: each owns two 4-pixel quads of a 32x32 tile
-constexpr int kTiledThreads = kConsumerThreads + 32;    // + producer warp
-constexpr int kTmapRows = 32;  // descriptor table index = (w16-1)*kTmapRows + (h8-1)
+constexpr int kRingMaxStages = 4;
+constexpr int kStaticTickets = 3;  // units a warp owns before it draws from the counter
 
-struct TiledParams {
+struct RingParams {
     const TileDesc *tiles;
     const uint8_t *entries;
-    const CUtensorMap *tmaps;
     const uint8_t *faces;
     size_t face_stride;
     const uint8_t *bg;
@@ -199,54 +198,27 @@ struct TiledParams {
     const uint32_t *rgba;
     void *out;
     size_t out_stride;
-    uint32_t ntiles, nframes, total;
+    uint32_t *ticket;       // monotonic counter (never reset: see launch_ring)
+    uint32_t ticket_base;   // its value when this launch starts
+    uint32_t nbox, ngather, ntiles;
+    uint32_t nframes, fchunk, nchunks, nunits;
+    uint32_t stage_bytes, nstages;
     int width, height;
-    uint32_t zero;  // always 0, but only the host knows: see stage_release()
-};
-
-struct __align__(128) TiledStage {
-    uint8_t box[kMaxBoxBytes];          // TMA destination; GATHER tiles put their 4 KB of 32-bit entries here instead
-    uint8_t entries[kTilePixels * 2];   // 16-bit entries of BOX tiles
-    uint4 desc;                         // TileDesc
-    uint32_t frame;
-    uint32_t pad[3];
+    uint32_t zero;  // always 0, but only the host knows: see stage_dep()
+    uint32_t lab;   // BLINKY_LAB experiment bits (0 in production): 1 no LDS, 2 no TMA, 4 no stores
+    uint32_t prefetch;  // L2 prefetch distance in boxes ahead of the TMA issue (0 = off)
+    int platesize;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Releases a pipeline stage AFTER the values read from it have really arrived in
-// registers.  A shared-memory load is only complete when its destination register is
-// written; `mbarrier.arrive` does not wait for in-flight LDS (seen in SASS: the arrive
-// issued right behind eight pending LDS, and the producer's next TMA then raced them).
-// Passing a value computed from every loaded register as an (unused) asm input makes
-// the scoreboard hold the arrive until those loads have landed.
-// Hands a ring stage back to the producer once EVERY lane of the warp has the stage's data in
-// registers.  `mbarrier.arrive` does not wait for shared-memory loads that are still in flight, and
-// when the LSU queue is backed up (slow stores to a peer GPU or to host memory) an LDS can sit there
-// long enough for the producer's next TMA to overwrite the stage under it.  An unused asm operand is
-// not a dependency either — ptxas drops the computation feeding it.  So the loaded values are folded,
-// through a kernel parameter that is always zero but unknown to the compiler, into the barrier's
-// ADDRESS: the warp-wide OR reduction needs every lane's loaded registers, the arrive needs its result.
-// CONVERGED: every lane executed the same load instructions (no divergence since the stage became
-// visible).  A warp-level load completes as a whole, so lane 0's registers stand for all lanes and the
-// reduction can be skipped.
-template <bool CONVERGED>
-__device__ __forceinline__ void stage_release(uint64_t *bar, uint32_t loaded_values, uint32_t zero, uint32_t lane) {
-    uint32_t dep = loaded_values & zero;
-    if (CONVERGED) __syncwarp();
-    else dep = __reduce_or_sync(0xffffffffu, dep);
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + dep) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -255,316 +227,349 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
+        "}" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
 // NB (measured on B200, scripts/tma_probe.cu): the innermost coordinate must be a
 // multiple of 16 bytes or the TMA unit raises "illegal instruction".
-__device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *tmap, int x, int y, int plate, int frame,
-                                             uint64_t *bar) {
+__device__ __forceinline__ void tma_load_box(uint32_t smem_dst, const CUtensorMap *tmap, int x, int y, int plate, int frame, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(plate), "r"(frame), "r"(smem_u32(bar))
+        ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(plate), "r"(frame), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
-// one quad (4 consecutive pixels) of a BOX tile: e2 holds its four 16-bit entries
-template <bool RUBIX, bool FULL>
-__device__ __forceinline__ void box_quad(const uint8_t *__restrict__ box, const uint8_t *__restrict__ s_lut, uint2 e2,
-                                         uint32_t (&px)[4], uint32_t &valid) {
-    const uint32_t ent[4] = {e2.x & 0xffffu, e2.x >> 16, e2.y & 0xffffu, e2.y >> 16};
-    valid = 0xfu;
-    if (!FULL) valid = ((ent[0] >> 15) & 1u) | ((ent[1] >> 14) & 2u) | ((ent[2] >> 13) & 4u) | ((ent[3] >> 12) & 8u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // unmapped entries carry offset 0: the read is harmless and its value is replaced below
-        uint32_t b = box[ent[k] & kBoxOffsetMask];
-        if (RUBIX) {
-            const uint32_t t = (ent[k] >> kBoxTintShift) & 7u;
-            if (t != BLINKY_LM_TINT_NONE) b = s_lut[t * 256 + b];
-        }
-        px[k] = b;
-    }
+// A ring stage may only be refilled once the bytes read from it sit in registers: a shared-memory
+// load is complete when its destination register is written, and neither `mbarrier` operations nor
+// a TMA issue wait for loads in flight (round 1, DESIGN "hardware findings" 2: with the LSU queue
+// backed up by slow peer/host stores an LDS waited long enough for the next TMA to overwrite the
+// stage under it).  So the values loaded from the stage are folded, through a kernel parameter that
+// is always zero but unknown to the compiler, into the ADDRESS operand of the refilling TMA.  The
+// warp is converged across the loads (they are unconditional), a warp-level load completes as a
+// whole, so lane 0's registers stand for all lanes.
+__device__ __forceinline__ uint32_t stage_dep(const uint32_t (&w)[8], uint32_t zero) {
+    return (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) & zero;
 }
 
-// GATHER tile (plate seams, singular points, strong minification): 32-bit entries,
-// direct global reads.  Layout differs from the BOX path on purpose: a warp takes
-// 8 tile rows and lane l is column l, so one warp-level load covers 32 consecutive
-// screen pixels of ONE row — neighbouring texels of at most a few plate rows —
-// instead of an 8x4 patch that touches 4x as many 32-byte sectors.
-template <bool RUBIX, bool RGBA>
-__device__ __forceinline__ void gather_tile(const TiledParams &p, const uint32_t *__restrict__ ent32, const uint8_t *__restrict__ faces,
-                                            const uint8_t *__restrict__ s_lut, const uint32_t *__restrict__ s_rgba, uint8_t *out_frame,
-                                            uint32_t tile_x, uint32_t tile_y, uint32_t warp, uint32_t lane, uint64_t *empty_bar,
-                                            uint32_t stage_words) {
-    uint32_t e[8], v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] = ent32[(warp * 8 + j) * kTileW + lane];
-    // entries are in registers: the stage can be refilled
-    stage_release<true>(empty_bar, e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7] | stage_words, p.zero, lane);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        v[j] = 0;
-        if (e[j] & BLINKY_LM_VALID) v[j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
-    }
-    const uint32_t x = tile_x + lane;
-    if (x >= static_cast<uint32_t>(p.width)) return;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t y = tile_y + warp * 8 + j;
-        if (y < static_cast<uint32_t>(p.height)) {
-            const uint32_t pix = y * static_cast<uint32_t>(p.width) + x;
-            uint32_t b = v[j];
-            if (e[j] & BLINKY_LM_VALID) {
-                if (RUBIX) {
-                    const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
-                    if (t != BLINKY_LM_TINT_NONE) b = s_lut[t * 256 + b];
-                }
-            } else {
-                b = __ldg(p.bg + pix);
-            }
-            if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[b];
-            else out_frame[pix] = static_cast<uint8_t>(b);
-        }
-    }
-}
+// One TMA descriptor per box shape of the plan, passed in the kernel's parameter block
+// (__grid_constant__): descriptors in param space need no tensormap-proxy fence, unlike a table in
+// global memory written by cudaMemcpy (a per-unit fence there drains every outstanding load of the
+// warp and invalidates the SM's descriptor cache: measured 6 us per unit).
+struct RingTmaps {
+    CUtensorMap m[kMaxShapes];
+};
 
-template <bool RGBA>
-__device__ __forceinline__ void store_quad(void *out_frame, const uint32_t *__restrict__ s_rgba, uint32_t quad_index,
-                                           const uint32_t (&px)[4]) {
-    if (RGBA) {
-        st_stream_v4(static_cast<uint4 *>(out_frame) + quad_index, make_uint4(s_rgba[px[0]], s_rgba[px[1]], s_rgba[px[2]], s_rgba[px[3]]));
-    } else {
-        st_stream_u32(static_cast<uint32_t *>(out_frame) + quad_index, pack4(px[0], px[1], px[2], px[3]));
-    }
-}
+struct RingUnit {     // what the warp knows about one of its upcoming units (all warp-uniform)
+    uint32_t ticket;  // unit index; >= nunits: none
+    uint32_t tile, f0, nf;
+    uint32_t dy, dz, dw;  // TileDesc words 1..3: box origin | plate, type/shape, box shape | tile origin
+};
 
-__device__ __forceinline__ void patch_background(const uint8_t *__restrict__ bg, uint32_t pix, uint32_t valid, uint32_t (&px)[4]) {
-    if (valid != 0xfu) {
-        const uint32_t bgw = __ldg(reinterpret_cast<const uint32_t *>(bg + pix));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (!((valid >> k) & 1u)) px[k] = (bgw >> (8 * k)) & 0xffu;
-    }
-}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <bool RUBIX, bool RGBA>
-__global__ void __launch_bounds__(kTiledThreads, 8) warp_tiled_kernel(const TiledParams p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    TiledStage *stages = reinterpret_cast<TiledStage *>(smem_raw);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + sizeof(TiledStage) * kStages);
-    uint64_t *empty_bar = full_bar + kStages;
-    uint8_t *s_lut = reinterpret_cast<uint8_t *>(empty_bar + kStages);
-    uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + 6 * 256);
-
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
-        }
+__global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant__ RingParams p, const __grid_constant__ RingTmaps tm) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t S = p.stage_bytes, D = p.nstages;
+    const uint32_t ring = smem_u32(smem_raw);
+    uint8_t *tail = smem_raw + static_cast<size_t>(S) * D;
+    const uint32_t bars = smem_u32(tail);
+    uint8_t *s_lut = tail + kRingMaxStages * 8;                       // [7][256]: 6 plate LUTs + identity
+    uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + (RUBIX ? 7 * 256 : 0));
+    if (lane == 0) {
+        for (uint32_t s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (RUBIX) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
-        for (int i = tid; i < 6 * 256 / 4; i += kTiledThreads) dst[i] = __ldg(src + i);
+        for (uint32_t i = lane; i < 6 * 256 / 4; i += 32) dst[i] = __ldg(src + i);
+        for (uint32_t i = lane; i < 64; i += 32) dst[6 * 64 + i] = (4 * i) * 0x01010101u + 0x03020100u;
     }
     if (RGBA) {
-        for (int i = tid; i < 256; i += kTiledThreads) s_rgba[i] = __ldg(p.rgba + i);
+        for (uint32_t i = lane; i < 256; i += 32) s_rgba[i] = __ldg(p.rgba + i);
     }
-    __syncthreads();
+    __syncwarp();
+    const uint32_t lut_base = smem_u32(s_lut);
 
-    const uint32_t G = gridDim.x;
-    if (tid >= kConsumerThreads) {
-        // ------------------------------ producer warp ------------------------------
-        if (tid == kConsumerThreads) {
-            uint32_t w = blockIdx.x;
-            uint4 next = make_uint4(0, 0, 0, 0);
-            if (w < p.total) next = __ldg(reinterpret_cast<const uint4 *>(p.tiles + w / p.nframes));
-            for (uint32_t it = 0; w < p.total; w += G, ++it) {
-                const uint32_t stage = it % kStages, round = it / kStages;
-                const uint4 d = next;
-                const uint32_t tile = w / p.nframes, frame = w - tile * p.nframes;
-                const uint32_t wn = w + G;
-                if (wn < p.total) next = __ldg(reinterpret_cast<const uint4 *>(p.tiles + wn / p.nframes));
-                if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1u);
-                TiledStage &st = stages[stage];
-                st.desc = d;
-                st.frame = frame;
-                const uint32_t type = (d.z >> 8) & 0xffu;
-                if (type == TILE_BOX || type == TILE_BOX_FULL) {
-                    const uint32_t w16 = (d.z >> 16) & 0xffu, h8 = d.z >> 24;
-                    const uint32_t box_bytes = w16 * 16u * h8 * 8u;
-                    mbar_expect_tx(&full_bar[stage], box_bytes + kTilePixels * 2);
-                    tma_load_box(st.box, p.tmaps + (w16 - 1) * kTmapRows + (h8 - 1), static_cast<int>(static_cast<int16_t>(d.y & 0xffffu)),
-                                 static_cast<int>(static_cast<int16_t>(d.y >> 16)), static_cast<int>(d.z & 0xffu),
-                                 static_cast<int>(frame), &full_bar[stage]);
-                    bulk_copy_g2s(st.entries, p.entries + d.x, kTilePixels * 2, &full_bar[stage]);
-                } else if (type == TILE_GATHER) {
-                    mbar_expect_tx(&full_bar[stage], kTilePixels * 4);
-                    bulk_copy_g2s(st.box, p.entries + d.x, kTilePixels * 4, &full_bar[stage]);
+    const uint32_t NW = gridDim.x;
+    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
+
+    auto describe = [&](uint32_t ticket) {
+        RingUnit u;
+        u.ticket = ticket;
+        u.tile = 0; u.f0 = 0; u.nf = 0;
+        u.dy = u.dz = u.dw = 0;
+        if (ticket < p.nunits) {
+            u.tile = ticket / p.nchunks;
+            const uint32_t chunk = ticket - u.tile * p.nchunks;
+            u.f0 = chunk * p.fchunk;
+            u.nf = min(p.fchunk, p.nframes - u.f0);
+            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + u.tile));
+            u.dy = d.y; u.dz = d.z; u.dw = d.w;
+        }
+        return u;
+    };
+    auto is_box = [&](const RingUnit &u) { return u.ticket < p.nunits && u.tile < p.nbox; };
+    // entry words of a BOX unit: 4 x 128 bit (+ 2 x 128 bit of tint bytes when the overlay is on)
+    auto load_box_entries = [&](const RingUnit &u, uint4 (&e)[4], uint4 (&t)[2]) {
+        if (is_box(u)) {
+            const uint8_t *blk = p.entries + static_cast<size_t>(u.tile) * kBoxBlockBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = ldg_nc_v4(blk + (k * 32 + lane) * 16);
+            if (RUBIX) {
+                t[0] = ldg_nc_v4(blk + kBoxEntryBytes + lane * 16);
+                t[1] = ldg_nc_v4(blk + kBoxEntryBytes + (32 + lane) * 16);
+            }
+        }
+    };
+
+    // ring state (warp-uniform)
+    uint32_t cs = 0, is = 0, phases = 0, inflight = 0;
+    auto issue_box = [&](uint32_t dy, uint32_t dz, uint32_t frame, uint32_t dep) {
+        if (lane == 0) {
+            const uint32_t w16 = (dz >> 16) & 0xffu, h8 = dz >> 24, shape = (dz >> (8 + kTileShapeShift)) & 63u;
+            const uint32_t bar = bars + 8 * is;
+            if (p.lab & 2u) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            } else {
+                mbar_expect_tx(bar, w16 * 16u * h8 * 8u);
+                tma_load_box(ring + is * S + dep, &tm.m[shape], static_cast<int>(static_cast<int16_t>(dy & 0xffffu)),
+                             static_cast<int>(static_cast<int16_t>(dy >> 16)), static_cast<int>(dz & 0xffu), static_cast<int>(frame), bar);
+            }
+        }
+        is = is + 1 == D ? 0 : is + 1;
+        ++inflight;
+    };
+    // L2 prefetch of a box some frames before its TMA load is issued: the TMA unit keeps a bounded number
+    // of row requests in flight, so what it can stream is (requests in flight) / latency — rows that
+    // already sit in L2 return three times sooner than rows that come from HBM (scripts/tma_lab.cu).
+    // One `prefetch.global.L2` per 128-byte line of each box row, rows spread over the lanes.
+    auto prefetch_box = [&](uint32_t dy, uint32_t dz, uint32_t frame) {
+        const int x = static_cast<int16_t>(dy & 0xffffu), y = static_cast<int16_t>(dy >> 16);
+        const int w = static_cast<int>((dz >> 16) & 0xffu) * 16, h = static_cast<int>(dz >> 24) * 8, ps = p.platesize;
+        const uint8_t *base = p.faces + static_cast<size_t>(frame) * p.face_stride + static_cast<size_t>(dz & 0xffu) * ps * ps;
+        const int x1 = min(x + w, ps) - 1;
+        for (int r = static_cast<int>(lane); r < h; r += 32) {
+            const int yy = y + r;
+            if (yy < 0 || yy >= ps) continue;
+            const uint8_t *row = base + static_cast<size_t>(yy) * ps;
+            for (int c = x & ~127; c <= x1; c += 128) prefetch_l2(row + max(c, x));
+        }
+    };
+
+    RingUnit A = describe(blockIdx.x), B = describe(blockIdx.x + NW), C = describe(blockIdx.x + 2 * NW);
+    uint4 eA[4], tA[2], eB[4], tB[2];
+    load_box_entries(A, eA, tA);
+    uint32_t issA = 0, issB = 0;  // boxes already issued for A / B
+    uint32_t pfA = 0, pfB = 0;    // boxes already prefetched into L2 for A / B
+    const uint32_t PF = p.prefetch;
+
+    while (A.ticket < p.nunits) {
+        // look ahead: next ticket (drawn only while the last known one was good, so that the number of
+        // draws per launch is a function of the launch alone), B's entries.  asm volatile keeps the draw
+        // HERE, a whole unit before its result is needed.
+        uint32_t drawn = 0xffffffffu - kStaticTickets * NW + p.ticket_base;  // -> next_ticket 0xffffffff when nothing is drawn
+        if (C.ticket < p.nunits && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(drawn) : "l"(p.ticket) : "memory");
+        load_box_entries(B, eB, tB);
+
+        const uint32_t type = (A.dz >> 8) & kTileTypeMask;
+        const uint32_t tile_x = A.dw & 0xffffu, tile_y = A.dw >> 16;
+        if (A.tile < p.nbox) {
+            // ---- unpack the lane's 32 entries once for all frames of the unit
+            uint32_t off[32];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w4[4] = {eA[k].x, eA[k].y, eA[k].z, eA[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    off[8 * k + 2 * j] = w4[j] & kBoxOffsetMask;
+                    off[8 * k + 2 * j + 1] = (w4[j] >> 16) & kBoxOffsetMask;
+                }
+            }
+            const bool full = type == TILE_BOX_FULL;
+            const bool b_box = is_box(B);
+            // pixels of quad q (0..7): row (lane>>3) + 4q, columns 4*(lane&7) .. +3
+            const uint32_t qx = tile_x + 4u * (lane & 7u), qy = tile_y + (lane >> 3);
+            uint32_t vmask[8], bgw[8];
+            uint32_t store_mask = 0xffu;
+            if (!full) {
+                store_mask = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t w0 = q & 1 ? eA[q >> 1].z : eA[q >> 1].x, w1 = q & 1 ? eA[q >> 1].w : eA[q >> 1].y;
+                    // valid bits (bit 15 of each 16-bit entry) -> byte masks
+                    uint32_t m = 0;
+                    if (w0 & 0x8000u) m |= 0x000000ffu;
+                    if (w0 & 0x80000000u) m |= 0x0000ff00u;
+                    if (w1 & 0x8000u) m |= 0x00ff0000u;
+                    if (w1 & 0x80000000u) m |= 0xff000000u;
+                    vmask[q] = m;
+                    const uint32_t y = qy + 4u * q;
+                    bgw[q] = 0;
+                    if (qx < width && y < height) {
+                        store_mask |= 1u << q;
+                        if (m != 0xffffffffu) bgw[q] = __ldg(reinterpret_cast<const uint32_t *>(p.bg + static_cast<size_t>(y) * width + qx)) & ~m;
+                    }
+                }
+            }
+            // one step of the look-ahead cursors: L2 prefetch runs PF boxes ahead of the TMA issue, the
+            // TMA issue up to D boxes ahead of the consumer; both walk A's frames, then B's first ones
+            auto advance = [&](uint32_t dep) {
+                if (inflight < D) {
+                    if (issA < A.nf) { issue_box(A.dy, A.dz, A.f0 + issA, dep); ++issA; }
+                    else if (b_box && issB < B.nf) { issue_box(B.dy, B.dz, B.f0 + issB, dep); ++issB; }
+                }
+                if (PF) {
+                    if (pfA < A.nf) { if (pfA < issA + PF) { prefetch_box(A.dy, A.dz, A.f0 + pfA); ++pfA; } }
+                    else if (b_box && pfB < B.nf && pfB < issB + PF + (A.nf - issA)) { prefetch_box(B.dy, B.dz, B.f0 + pfB); ++pfB; }
+                }
+            };
+            if (pfA < issA) pfA = issA;
+            while (inflight < D && issA < A.nf) advance(0);
+            for (uint32_t f = 0; f < A.nf; ++f) {
+                mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
+                const uint32_t base = ring + cs * S;
+                uint32_t b[32];
+                if (p.lab & 1u) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) b[i] = off[i] & 255u;
                 } else {
-                    mbar_arrive(&full_bar[stage]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) b[i] = lds_u8(base + off[i]);
+                }
+                if (RUBIX) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint4 &tv = tA[i >> 4];
+                        const uint32_t tw = ((i >> 2) & 3) == 0 ? tv.x : ((i >> 2) & 3) == 1 ? tv.y : ((i >> 2) & 3) == 2 ? tv.z : tv.w;
+                        // (tint byte << 8) + pixel value indexes the [7][256] LUT
+                        b[i] = lds_u8(lut_base + __byte_perm(tw, 0, 0x4404 | ((i & 3) << 4)) + b[i]);
+                    }
+                }
+                uint32_t w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+                const uint32_t dep = stage_dep(w, p.zero);
+                phases ^= 1u << cs;
+                cs = cs + 1 == D ? 0 : cs + 1;
+                --inflight;
+                // refill: this unit's next frame, else the first frames of the next BOX unit
+                advance(dep);
+                uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
+                if ((p.lab & 4u) && w[0] + w[7] != 12345u) continue;
+                if (full) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const size_t pix = static_cast<size_t>(qy + 4u * q) * width + qx;
+                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(out_frame) + (pix >> 2),
+                                               make_uint4(s_rgba[b[4 * q]], s_rgba[b[4 * q + 1]], s_rgba[b[4 * q + 2]], s_rgba[b[4 * q + 3]]));
+                        else st_stream_u32(reinterpret_cast<uint32_t *>(out_frame) + (pix >> 2), w[q]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (!((store_mask >> q) & 1u)) continue;
+                        const size_t pix = static_cast<size_t>(qy + 4u * q) * width + qx;
+                        const uint32_t v = (w[q] & vmask[q]) | bgw[q];
+                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(out_frame) + (pix >> 2),
+                                               make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
+                        else st_stream_u32(reinterpret_cast<uint32_t *>(out_frame) + (pix >> 2), v);
+                    }
                 }
             }
-        }
-        return;
-    }
-
-    // -------------------------------- consumers --------------------------------
-    // thread t owns quad (row t/8, column t%8) and the quad 16 rows below it
-    const uint32_t qx4 = (tid & 7u) * 4u, row = tid >> 3, lane = tid & 31u;
-    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
-    uint32_t it = 0;
-    for (uint32_t w = blockIdx.x; w < p.total; w += G, ++it) {
-        const uint32_t stage = it % kStages, round = it / kStages;
-        TiledStage &st = stages[stage];
-        mbar_wait(&full_bar[stage], round & 1u);
-        const uint4 d = st.desc;
-        const uint32_t frame = st.frame;
-        const uint32_t type = (d.z >> 8) & 0xffu;
-        const uint32_t x = (d.w & 0xffffu) + qx4, y0 = (d.w >> 16) + row;
-        const uint32_t pix0 = y0 * width + x, pix1 = pix0 + 16u * width;
-        uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
-
-        uint32_t pa[4], pb[4], va = 0, vb = 0;
-        if (type == TILE_BOX_FULL) {
-            const uint2 ea = reinterpret_cast<const uint2 *>(st.entries)[tid];
-            const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
-            box_quad<RUBIX, true>(st.box, s_lut, ea, pa, va);
-            box_quad<RUBIX, true>(st.box, s_lut, eb, pb, vb);
-            stage_release<true>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
-            store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
-            store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
-            continue;
-        }
-        if (type == TILE_BOX) {
-            const uint2 ea = reinterpret_cast<const uint2 *>(st.entries)[tid];
-            const uint2 eb = reinterpret_cast<const uint2 *>(st.entries)[tid + kConsumerThreads];
-            box_quad<RUBIX, false>(st.box, s_lut, ea, pa, va);
-            box_quad<RUBIX, false>(st.box, s_lut, eb, pb, vb);
-        } else if (type == TILE_GATHER) {
-            gather_tile<RUBIX, RGBA>(p, reinterpret_cast<const uint32_t *>(st.box), p.faces + static_cast<size_t>(frame) * p.face_stride,
-                                     s_lut, s_rgba, out_frame, d.w & 0xffffu, d.w >> 16, tid >> 5, lane, &empty_bar[stage],
-                                     d.w | frame);  // the descriptor words read from the stage count too
-            continue;
+        } else if (A.tile < p.nbox + p.ngather) {
+            // ---- GATHER: lane = column, 32 rows; entries are read here (no prefetch: 32 registers)
+            const uint32_t *ent32 = reinterpret_cast<const uint32_t *>(p.entries + static_cast<size_t>(p.nbox) * kBoxBlockBytes +
+                                                                       static_cast<size_t>(A.tile - p.nbox) * kGatherBlockBytes);
+            uint32_t e[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) e[r] = __ldg(ent32 + r * kTileW + lane);
+            const uint32_t x = tile_x + lane;
+            if (x < width) {
+                uint32_t rows = min(32u, height - tile_y);
+                // unmapped pixels take the background once per unit
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    if (!(e[r] & BLINKY_LM_VALID)) {
+                        uint32_t bgv = 0;
+                        if (static_cast<uint32_t>(r) < rows) bgv = __ldg(p.bg + static_cast<size_t>(tile_y + r) * width + x);
+                        e[r] = bgv;  // valid bit clear, low byte = background value
+                    }
+                }
+                for (uint32_t f = 0; f < A.nf; ++f) {
+                    const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(A.f0 + f) * p.face_stride;
+                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        v[r] = e[r] & 0xffu;
+                        if (e[r] & BLINKY_LM_VALID) v[r] = ld_face(faces + (e[r] & BLINKY_LM_INDEX_MASK));
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        if (static_cast<uint32_t>(r) >= rows) break;
+                        uint32_t bv = v[r];
+                        if (RUBIX && (e[r] & BLINKY_LM_VALID)) {
+                            const uint32_t t = (e[r] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                            if (t != BLINKY_LM_TINT_NONE) bv = s_lut[t * 256 + bv];
+                        }
+                        const size_t pix = static_cast<size_t>(tile_y + r) * width + x;
+                        if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[bv];
+                        else out_frame[pix] = static_cast<uint8_t>(bv);
+                    }
+                }
+            }
         } else {
+            // ---- EMPTY: background only (quad layout)
+            const uint32_t qx = tile_x + 4u * (lane & 7u), qy = tile_y + (lane >> 3);
+            if (qx < width) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) pa[k] = pb[k] = 0;
-        }
-        // everything this warp needs from the stage is in registers: hand the stage back
-        stage_release<false>(&empty_bar[stage], pa[0] | pa[1] | pa[2] | pa[3] | pb[0] | pb[1] | pb[2] | pb[3] | d.w | frame, p.zero, lane);
-        if (x < width) {
-            if (y0 < height) {
-                patch_background(p.bg, pix0, va, pa);
-                store_quad<RGBA>(out_frame, s_rgba, pix0 >> 2, pa);
-            }
-            if (y0 + 16u < height) {
-                patch_background(p.bg, pix1, vb, pb);
-                store_quad<RGBA>(out_frame, s_rgba, pix1 >> 2, pb);
-            }
-        }
-    }
-}
-
-
-// --------------------------------------------------------------------------
-// K3: companion of K2 for the tiles TMA staging cannot serve (GATHER: plate seams,
-// singular points, strong minification; EMPTY: background only).  These are bound
-// by global-memory latency, so instead of the ring they get plain parallelism:
-// grid = (tiles, frame groups), 256 threads, a warp owns 4 tile rows and lane l is
-// column l (one warp-level load = 32 consecutive screen pixels of one row).  The
-// tile's entries are fetched once and reused for every frame of the group.
-// --------------------------------------------------------------------------
-constexpr int kGatherFramesPerCta = 4;
-
-template <bool RUBIX, bool RGBA>
-__global__ void __launch_bounds__(kThreads) warp_tile_gather_kernel(const TiledParams p, const uint32_t first_tile) {
-    const uint32_t tid = threadIdx.x;
-    const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + first_tile + blockIdx.x));
-    const uint32_t type = (d.z >> 8) & 0xffu;
-    const uint32_t tile_x = d.w & 0xffffu, tile_y = d.w >> 16;
-    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
-    const uint32_t f0 = blockIdx.y * kGatherFramesPerCta;
-    const uint32_t f1 = min(f0 + kGatherFramesPerCta, p.nframes);
-
-    if (type == TILE_EMPTY) {
-        // quad layout: thread t copies 4 background pixels of row t/8
-        const uint32_t x = tile_x + (tid & 7u) * 4u, y = tile_y + (tid >> 3);
-        if (x >= width || y >= height) return;
-        const uint32_t pix = y * width + x;
-        const uint32_t bgw = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
-        const uint32_t px[4] = {bgw & 0xffu, (bgw >> 8) & 0xffu, (bgw >> 16) & 0xffu, bgw >> 24};
-        for (uint32_t f = f0; f < f1; ++f) {
-            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
-            if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(o) + (pix >> 2), make_uint4(__ldg(p.rgba + px[0]), __ldg(p.rgba + px[1]), __ldg(p.rgba + px[2]), __ldg(p.rgba + px[3])));
-            else st_stream_u32(reinterpret_cast<uint32_t *>(o) + (pix >> 2), bgw);
-        }
-        return;
-    }
-
-    const uint32_t warp = tid >> 5, lane = tid & 31u;
-    const uint32_t x = tile_x + lane;
-    const uint32_t *__restrict__ ent32 = reinterpret_cast<const uint32_t *>(p.entries + d.x);
-    uint32_t e[4], bgv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) e[j] = __ldg(ent32 + (warp * 4 + j) * kTileW + lane);
-    if (x >= width) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t y = tile_y + warp * 4 + j;
-        bgv[j] = 0;
-        if (!(e[j] & BLINKY_LM_VALID) && y < height) bgv[j] = __ldg(p.bg + y * width + x);
-    }
-    // all gathers of the CTA's frames are issued before the first store: 16 independent
-    // loads in flight per thread instead of 4 (stores may alias loads as far as the compiler
-    // knows, so a plain frame loop would serialise on them)
-    uint32_t v[kGatherFramesPerCta][4];
-#pragma unroll
-    for (int g = 0; g < kGatherFramesPerCta; ++g) {
-        const uint32_t f = f0 + g;
-        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f < f1 ? f : f0) * p.face_stride;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[g][j] = bgv[j];
-            if (e[j] & BLINKY_LM_VALID) v[g][j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < kGatherFramesPerCta; ++g) {
-        const uint32_t f = f0 + g;
-        if (f >= f1) break;
-        uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t y = tile_y + warp * 4 + j;
-            if (y < height) {
-                uint32_t b = v[g][j];
-                if (RUBIX && (e[j] & BLINKY_LM_VALID)) {
-                    const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
-                    if (t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t y = qy + 4u * q;
+                    if (y >= height) break;
+                    const size_t pix = static_cast<size_t>(y) * width + qx;
+                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
+                    for (uint32_t f = 0; f < A.nf; ++f) {
+                        uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
+                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(out_frame) + (pix >> 2),
+                                               make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
+                        else st_stream_u32(reinterpret_cast<uint32_t *>(out_frame) + (pix >> 2), v);
+                    }
                 }
-                const uint32_t pix = y * width + x;
-                if (RGBA) reinterpret_cast<uint32_t *>(o)[pix] = __ldg(p.rgba + b);
-                else o[pix] = static_cast<uint8_t>(b);
             }
         }
+        // rotate: A <- B <- C <- the ticket drawn above
+        const uint32_t next_ticket = kStaticTickets * NW + (__shfl_sync(0xffffffffu, drawn, 0) - p.ticket_base);
+        A = B;
+        B = C;
+        C = describe(next_ticket);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eA[k] = eB[k];
+        tA[0] = tB[0];
+        tA[1] = tB[1];
+        issA = issB;
+        issB = 0;
+        pfA = pfB;
+        pfB = 0;
     }
 }
-
-constexpr size_t kTiledSmemBytes = sizeof(TiledStage) * kStages + 2 * kStages * sizeof(uint64_t) + 6 * 256 + 256 * 4;
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -611,11 +616,11 @@ struct WarpDevice::Slot {
     bool keep_unmapped = false, direct = false;
 };
 
-struct WarpDevice::TmapSet {
+struct WarpDevice::TmapSet {   // host-side: the descriptors travel in the kernel's parameter block
     const void *faces = nullptr;
     size_t face_stride = 0;
     int nframes = 0;
-    CUtensorMap *d_table = nullptr;  // [8 * kTmapRows]
+    RingTmaps table;
     uint64_t last_use = 0;
 };
 
@@ -651,6 +656,11 @@ WarpDevice::WarpDevice(int device) : device_(device) {
     sm_count_ = prop.multiProcessorCount;
     if (const char *e = getenv("BLINKY_E2E_UPLOAD")) upload_by_kernel_ = strcmp(e, "kernel") == 0;
     if (const char *e = getenv("BLINKY_E2E_OUT")) out_by_kernel_ = strcmp(e, "direct") == 0;
+    if (const char *e = getenv("BLINKY_RING_STAGES")) ring_stages_ = atoi(e);
+    if (const char *e = getenv("BLINKY_RING_CTAS")) ring_ctas_cap_ = atoi(e);
+    if (const char *e = getenv("BLINKY_FCHUNK")) fchunk_ = atoi(e);
+    if (const char *e = getenv("BLINKY_PREFETCH")) prefetch_ = atoi(e);
+    if (const char *e = getenv("BLINKY_L2_PROMOTION")) l2_promotion_ = atoi(e) & 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B
     cudaStream_t s;
     e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -680,10 +690,8 @@ WarpDevice::~WarpDevice() {
     cudaFree(d_rgba_);
     cudaFree(d_tiles_);
     cudaFree(d_entries_);
-    for (TmapSet *t : tmap_sets_) {
-        cudaFree(t->d_table);
-        delete t;
-    }
+    for (TmapSet *t : tmap_sets_) delete t;
+    for (TicketCounter &c : tickets_) cudaFree(c.d_counter);
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
 }
 
@@ -726,10 +734,7 @@ bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
     cudaFree(d_entries_);
     d_tiles_ = nullptr;
     d_entries_ = nullptr;
-    for (TmapSet *t : tmap_sets_) {
-        cudaFree(t->d_table);
-        delete t;
-    }
+    for (TmapSet *t : tmap_sets_) delete t;
     tmap_sets_.clear();
     if (lm.plan && !lm.plan->tiles.empty()) {
         const TilePlan &pl = *lm.plan;
@@ -739,6 +744,8 @@ bool WarpDevice::upload_lensmap(const LensmapUpload &lm) {
         CK(cudaMemcpy(d_entries_, pl.entries.data(), pl.entries.size(), cudaMemcpyHostToDevice));
         ntiles_ = static_cast<uint32_t>(pl.tiles.size());
         nbox_tiles_ = static_cast<uint32_t>(pl.n_box);
+        ngather_tiles_ = static_cast<uint32_t>(pl.n_gather);
+        stage_bytes_ = pl.stage_bytes;
         shapes_ = pl.shapes;
         plan_has_box_ = pl.n_box > 0;
         have_plan_ = true;
@@ -793,17 +800,20 @@ bool WarpDevice::warp(const void *d_faces, size_t face_stride, void *d_out, size
         return false;
     }
     const size_t opx = rgba ? 4 : 1;
+    if (rgba && (reinterpret_cast<uintptr_t>(d_out) % 4 != 0 || (nframes > 1 && out_stride % 4 != 0))) {
+        err_ = "warp (RGBA): the output buffer and the frame stride must be 4-byte aligned";
+        return false;
+    }
     // the tiled kernel writes 4-pixel words at (y*W + x): needs W % 4 == 0 and aligned frames
     const bool tiled_ok = have_plan_ && (width_ % 4 == 0) && (reinterpret_cast<uintptr_t>(d_out) % (4 * opx) == 0) &&
                           (out_stride % (4 * opx) == 0 || nframes == 1) &&
                           (!plan_has_box_ || (reinterpret_cast<uintptr_t>(d_faces) % 16 == 0 && (face_stride % 16 == 0 || nframes == 1)));
     if (variant_ == BLINKY_KERNEL_GATHER || !tiled_ok) return launch_flat(d_faces, face_stride, d_out, out_stride, nframes, stream, rgba);
-    return launch_tiled(d_faces, face_stride, d_out, out_stride, nframes, stream, rgba);
+    return launch_ring(d_faces, face_stride, d_out, out_stride, nframes, stream, rgba);
 }
 
-WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stride, int nframes, void *stream) {
-    static uint64_t tick = 0;
-    ++tick;
+WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stride, int nframes) {
+    const uint64_t tick = ++tmap_tick_;
     for (TmapSet *t : tmap_sets_)
         if (t->faces == d_faces && t->face_stride == face_stride && t->nframes == nframes) {
             t->last_use = tick;
@@ -820,39 +830,31 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
         encode_fn_ = fn;
     }
     TmapSet *t = nullptr;
-    if (tmap_sets_.size() >= 8) {  // recycle the least recently used table (its kernels are long gone)
+    if (tmap_sets_.size() >= 32) {  // host memory only (a launch copies its table into the parameter block): recycle the oldest
         t = tmap_sets_[0];
         for (TmapSet *c : tmap_sets_)
             if (c->last_use < t->last_use) t = c;
-        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     } else {
         t = new TmapSet();
-        if (cudaMalloc(&t->d_table, sizeof(CUtensorMap) * 8 * kTmapRows) != cudaSuccess) {
-            delete t;
-            fail("cudaMalloc(tensor maps)", cudaGetLastError());
-            return nullptr;
-        }
         tmap_sets_.push_back(t);
     }
     t->faces = d_faces;
     t->face_stride = face_stride;
     t->nframes = nframes;
     t->last_use = tick;
-    std::vector<CUtensorMap> host(8 * kTmapRows);
-    memset(host.data(), 0, host.size() * sizeof(CUtensorMap));
+    memset(&t->table, 0, sizeof t->table);
     const cuuint64_t ps = static_cast<cuuint64_t>(platesize_);
     // 4-D view of the globe: (x, y, plate, frame)
     const cuuint64_t dims[4] = {ps, ps, static_cast<cuuint64_t>(numplates_), static_cast<cuuint64_t>(nframes)};
     const cuuint64_t fstride = nframes > 1 ? static_cast<cuuint64_t>(face_stride) : ps * ps * static_cast<cuuint64_t>(numplates_);
     const cuuint64_t strides[3] = {ps, ps * ps, fstride};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (uint16_t shape : shapes_) {
-        const uint32_t w16 = shape >> 8, h8 = shape & 0xff;
+    for (size_t si = 0; si < shapes_.size() && si < static_cast<size_t>(kMaxShapes); ++si) {
+        const uint32_t w16 = shapes_[si] >> 8, h8 = shapes_[si] & 0xff;
         const cuuint32_t box[4] = {w16 * 16, h8 * 8, 1, 1};
         CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
-            &host[(w16 - 1) * kTmapRows + (h8 - 1)], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(d_faces), dims, strides,
-            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            &t->table.m[si], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(d_faces), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, static_cast<CUtensorMapL2promotion>(l2_promotion_), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             char buf[160];
             snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(box %ux%u, ps %d) failed with CUresult %d", w16 * 16, h8 * 8, platesize_, static_cast<int>(r));
@@ -861,26 +863,28 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
             return nullptr;
         }
     }
-    if (cudaMemcpyAsync(t->d_table, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
-                        static_cast<cudaStream_t>(stream)) != cudaSuccess) {
-        fail("cudaMemcpyAsync(tensor maps)", cudaGetLastError());
-        t->faces = nullptr;
-        return nullptr;
-    }
     return t;
 }
 
-bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
-                              void *stream, bool rgba) {
+template <bool RUBIX, bool RGBA>
+static cudaError_t ring_config(size_t smem, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA>, 32, smem);
+}
+
+bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
+                             void *stream, bool rgba) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TiledParams p;
+    RingParams p;
     p.tiles = static_cast<const TileDesc *>(d_tiles_);
     p.entries = d_entries_;
-    p.tmaps = nullptr;
+    static const RingTmaps kNoTmaps = {};
+    const RingTmaps *tm = &kNoTmaps;
     if (plan_has_box_) {
-        TmapSet *t = get_tmaps(d_faces, face_stride, nframes, stream);
+        TmapSet *t = get_tmaps(d_faces, face_stride, nframes);
         if (!t) return false;
-        p.tmaps = t->d_table;
+        tm = &t->table;
     }
     p.faces = static_cast<const uint8_t *>(d_faces);
     p.face_stride = face_stride;
@@ -889,60 +893,89 @@ bool WarpDevice::launch_tiled(const void *d_faces, size_t face_stride, void *d_o
     p.rgba = d_rgba_;
     p.out = d_out;
     p.out_stride = out_stride;
-    // Tiles [0, nbox) are BOX tiles.  When only a few tiles are GATHER/EMPTY they ride along
-    // in the TMA ring (one launch; their global latency hides among the BOX tiles); when
-    // they are many (strong minification, big unmapped borders) they go to the gather
-    // kernel K3, which hides that latency with plain parallelism.
-    const bool split = (ntiles_ - nbox_tiles_) * 100u > ntiles_ * static_cast<uint32_t>(split_percent_);
-    const uint32_t ring_tiles = split ? nbox_tiles_ : ntiles_;
-    p.ntiles = ring_tiles;
+    p.nbox = nbox_tiles_;
+    p.ngather = ngather_tiles_;
+    p.ntiles = ntiles_;
     p.nframes = static_cast<uint32_t>(nframes);
-    p.total = ring_tiles * static_cast<uint32_t>(nframes);
     p.width = width_;
     p.height = height_;
     p.zero = 0;
+    p.lab = 0;
+    if (const char *e = getenv("BLINKY_LAB")) p.lab = static_cast<uint32_t>(atoi(e));
+    p.prefetch = static_cast<uint32_t>(prefetch_);
+    p.platesize = platesize_;
     const bool rubix = rubix_;
     const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
-    if (tiled_ctas_per_sm_[vi] == 0) {
+    // ring geometry: stages hold the plan's largest box
+    p.stage_bytes = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
+    p.nstages = ring_stages_ > 0 ? static_cast<uint32_t>(ring_stages_) : (p.stage_bytes <= 4096 ? 3u : 2u);
+    if (p.nstages > static_cast<uint32_t>(kRingMaxStages)) p.nstages = kRingMaxStages;
+    const size_t smem = static_cast<size_t>(p.stage_bytes) * p.nstages + kRingMaxStages * 8 + (rubix ? 7 * 256 : 0) + (rgba ? 1024 : 0);
+    if (ring_ctas_per_sm_[vi] == 0 || ring_smem_[vi] != smem) {
         int n = 0;
-        cudaError_t e;
-        const void *fn = rubix && rgba ? reinterpret_cast<const void *>(warp_tiled_kernel<true, true>)
-                         : rubix       ? reinterpret_cast<const void *>(warp_tiled_kernel<true, false>)
-                         : rgba        ? reinterpret_cast<const void *>(warp_tiled_kernel<false, true>)
-                                       : reinterpret_cast<const void *>(warp_tiled_kernel<false, false>);
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTiledSmemBytes));
-        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(max dynamic smem)", e);
-        if (rubix && rgba) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<true, true>, kTiledThreads, kTiledSmemBytes);
-        else if (rubix) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<true, false>, kTiledThreads, kTiledSmemBytes);
-        else if (rgba) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<false, true>, kTiledThreads, kTiledSmemBytes);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, warp_tiled_kernel<false, false>, kTiledThreads, kTiledSmemBytes);
-        if (e != cudaSuccess || n < 1) n = 4;
-        tiled_ctas_per_sm_[vi] = n;
+        cudaError_t e = rubix && rgba ? ring_config<true, true>(smem, &n)
+                        : rubix       ? ring_config<true, false>(smem, &n)
+                        : rgba        ? ring_config<false, true>(smem, &n)
+                                      : ring_config<false, false>(smem, &n);
+        if (e != cudaSuccess) return fail("ring kernel configuration (shared memory / occupancy)", e);
+        if (n < 1) {
+            err_ = "ring kernel does not fit on an SM";
+            return false;
+        }
+        ring_ctas_per_sm_[vi] = n;
+        ring_smem_[vi] = smem;
     }
-    uint32_t grid = static_cast<uint32_t>(sm_count_ * tiled_ctas_per_sm_[vi]);
-    if (grid > p.total) grid = p.total;
+    int ctas = ring_ctas_per_sm_[vi];
+    if (ring_ctas_cap_ > 0 && ctas > ring_ctas_cap_) ctas = ring_ctas_cap_;
+    uint32_t grid = static_cast<uint32_t>(sm_count_ * ctas);
+    // frames per unit: enough units per warp for the dynamic schedule to balance, few enough that a
+    // unit's entry unpack is spread over several frames
+    uint32_t fchunk = fchunk_ > 0 ? static_cast<uint32_t>(fchunk_) : static_cast<uint32_t>(static_cast<uint64_t>(nframes) * ntiles_ / (12ull * grid));
+    if (fchunk < 1) fchunk = 1;
+    if (fchunk_ <= 0 && fchunk > 8) fchunk = 8;
+    if (fchunk > p.nframes) fchunk = p.nframes;
+    p.fchunk = fchunk;
+    p.nchunks = (p.nframes + fchunk - 1) / fchunk;
+    p.nunits = ntiles_ * p.nchunks;
+    if (grid > p.nunits) grid = p.nunits;
+    if (grid == 0) return true;
+    // ticket counter of this stream (launches on one stream are serialised; the counter is never reset:
+    // the kernel subtracts the value it had when the launch started)
+    TicketCounter *tc = nullptr;
+    for (TicketCounter &c : tickets_)
+        if (c.stream == stream) tc = &c;
+    if (!tc) {
+        if (tickets_.size() >= 64) {  // streams come and go: start over
+            CK(cudaDeviceSynchronize());
+            for (TicketCounter &c : tickets_) cudaFree(c.d_counter);
+            tickets_.clear();
+        }
+        TicketCounter c;
+        c.stream = stream;
+        c.base = 0;
+        CK(cudaMalloc(&c.d_counter, sizeof(uint32_t)));
+        CK(cudaMemsetAsync(c.d_counter, 0, sizeof(uint32_t), st));
+        tickets_.push_back(c);
+        tc = &tickets_.back();
+    }
+    p.ticket = tc->d_counter;
+    p.ticket_base = tc->base;
+    // draws of this launch: every unit beyond the static ones is drawn once, and every warp whose last
+    // static ticket was good draws exactly one ticket past the end
+    const uint64_t nstatic = static_cast<uint64_t>(kStaticTickets) * grid;
+    const uint32_t good = p.nunits > nstatic ? static_cast<uint32_t>(p.nunits - nstatic) : 0u;
+    const uint64_t two = static_cast<uint64_t>(kStaticTickets - 1) * grid;
+    const uint32_t drawers = p.nunits > two ? static_cast<uint32_t>(std::min<uint64_t>(p.nunits - two, grid)) : 0u;
+    tc->base += good + drawers;
+
+    if (rubix && rgba) warp_ring_kernel<true, true><<<grid, 32, smem, st>>>(p, *tm);
+    else if (rubix) warp_ring_kernel<true, false><<<grid, 32, smem, st>>>(p, *tm);
+    else if (rgba) warp_ring_kernel<false, true><<<grid, 32, smem, st>>>(p, *tm);
+    else warp_ring_kernel<false, false><<<grid, 32, smem, st>>>(p, *tm);
+    ++launches_;
     char buf[320];
-    int n = 0;
-    if (p.total > 0) {
-        if (rubix && rgba) warp_tiled_kernel<true, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-        else if (rubix) warp_tiled_kernel<true, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-        else if (rgba) warp_tiled_kernel<false, true><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-        else warp_tiled_kernel<false, false><<<grid, kTiledThreads, kTiledSmemBytes, st>>>(p);
-        ++launches_;
-        n = snprintf(buf, sizeof buf, "warp_tiled_kernel<rubix=%d,rgba=%d> grid=%u block=%d (%d CTAs/SM, persistent, %d-stage TMA ring)", rubix, rgba,
-                     grid, kTiledThreads, tiled_ctas_per_sm_[vi], kStages);
-    }
-    const uint32_t nother = ntiles_ - ring_tiles;
-    if (nother > 0) {
-        dim3 g2(nother, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
-        if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else if (rubix) warp_tile_gather_kernel<true, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else if (rgba) warp_tile_gather_kernel<false, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else warp_tile_gather_kernel<false, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        ++launches_;
-        snprintf(buf + n, sizeof buf - static_cast<size_t>(n), "%swarp_tile_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", n ? " + " : "", rubix, rgba,
-                 g2.x, g2.y, kThreads);
-    }
+    snprintf(buf, sizeof buf, "warp_ring_kernel<rubix=%d,rgba=%d> grid=%u block=32 (%d warps/SM, %u-stage TMA ring of %u B, %u frames/unit, %u units)", rubix,
+             rgba, grid, ctas, p.nstages, p.stage_bytes, fchunk, p.nunits);
     last_kernel_ = buf;
     CK(cudaGetLastError());
     return true;

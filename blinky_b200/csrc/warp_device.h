@@ -90,21 +90,32 @@ private:
     std::vector<int32_t> span_off_, spans_;
     int variant_ = 0;
 
-    // tiled layout (kernel K2)
+    // tiled layout (ring kernel)
     struct TmapSet;
+    struct TicketCounter {
+        void *stream = nullptr;
+        uint32_t *d_counter = nullptr;
+        uint32_t base = 0;  // value the counter will have when the next launch on this stream starts
+    };
     bool have_plan_ = false;
     bool plan_has_box_ = false;
     void *d_tiles_ = nullptr;       // TileDesc[]
     uint8_t *d_entries_ = nullptr;
-    uint32_t ntiles_ = 0, nbox_tiles_ = 0;
-    int split_percent_ = 12;  // GATHER+EMPTY share of tiles above which they get their own kernel
+    uint32_t ntiles_ = 0, nbox_tiles_ = 0, ngather_tiles_ = 0;
+    int stage_bytes_ = 0;                // largest staged box of the plan
+    int prefetch_ = 0;                   // L2 prefetch distance of the ring kernel, boxes (BLINKY_PREFETCH)
+    int l2_promotion_ = 0;               // CUtensorMapL2promotion of the box descriptors (BLINKY_L2_PROMOTION)
+    int ring_stages_ = 0, ring_ctas_cap_ = 0, fchunk_ = 0;  // tuning overrides (BLINKY_RING_STAGES / _CTAS, BLINKY_FCHUNK); 0 = automatic
     std::vector<uint16_t> shapes_;
     std::vector<TmapSet *> tmap_sets_;   // small cache keyed by (faces ptr, stride, nframes)
+    uint64_t tmap_tick_ = 0;
+    std::vector<TicketCounter> tickets_; // one work counter per stream the ring kernel was launched on
     void *encode_fn_ = nullptr;          // cuTensorMapEncodeTiled
-    int tiled_ctas_per_sm_[4] = {0, 0, 0, 0};
-    TmapSet *get_tmaps(const void *d_faces, size_t face_stride, int nframes, void *stream);
-    bool launch_tiled(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
-                      bool rgba);
+    int ring_ctas_per_sm_[4] = {0, 0, 0, 0};
+    size_t ring_smem_[4] = {0, 0, 0, 0};
+    TmapSet *get_tmaps(const void *d_faces, size_t face_stride, int nframes);
+    bool launch_ring(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
+                     bool rgba);
     bool launch_flat(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes, void *stream,
                      bool rgba);
     std::string plan_summary_;

@@ -70,8 +70,7 @@ enum { BLINKY_MAP_NONE = 0, BLINKY_MAP_INVERSE = 1, BLINKY_MAP_FORWARD = 2 };
 enum {
     BLINKY_KERNEL_AUTO = 0,    /* pick per lensmap from the tile classification */
     BLINKY_KERNEL_GATHER = 1,  /* direct global gather, vectorised coalesced stores */
-    BLINKY_KERNEL_TMA = 2,     /* TMA-staged face tiles in shared memory where tiles are coherent */
-    BLINKY_KERNEL_COMPACT = 3  /* warp-shuffle compaction of scattered face reads */
+    BLINKY_KERNEL_TMA = 2      /* ring kernel: TMA-staged face tiles in shared memory where tiles are coherent (what AUTO picks) */
 };
 
 typedef struct blinky_ctx blinky_ctx;
@@ -240,6 +239,37 @@ int blinky_ipc_export(blinky_ctx *ctx, void *device_ptr, unsigned char handle[64
 int blinky_ipc_open(blinky_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
 int blinky_ipc_close(blinky_ctx *ctx, void *peer_ptr);
 
+/* ---- sharded batches: frames over N GPUs, finished frames gathered on rank 0 -----------------
+ * One process per GPU, one context per process.  A batch of total_frames independent frames is cut
+ * into contiguous blocks (blinky_shard_range, sizes differ by at most one); every rank builds the same
+ * lensmap and warps its own block; there is NO collective on the data path.  The reference topology's
+ * last step — finished frames reach the one display (the reference writes vid.buffer,
+ * engine/NQ/fisheye.c:802-803, 2406-2424) — is a gather to rank 0, done chunk by chunk so that the
+ * transfer of chunk k overlaps the warp of chunk k+1 (a compute and a communication stream per rank).
+ *   BLINKY_GATHER_NCCL        ncclSend / ncclRecv of finished chunks (NCCL only for the final gather)
+ *   BLINKY_GATHER_PEER_COPY   copy engines push finished chunks into rank 0's buffer (CUDA-IPC peer memory over NVLink)
+ *   BLINKY_GATHER_PEER_STORE  the warp kernels store straight into rank 0's buffer (fused warp + gather)
+ * NCCL is loaded at run time (libnccl.so.2, or the path in BLINKY_NCCL_LIB); the 128-byte id made by
+ * blinky_shard_unique_id on one rank is carried to the others by the caller (MPI, a file, torch.distributed ...).
+ * Calls marked collective must be made by every rank. */
+enum { BLINKY_GATHER_NCCL = 0, BLINKY_GATHER_PEER_COPY = 1, BLINKY_GATHER_PEER_STORE = 2 };
+/* pure arithmetic (no context): frames [*first, *first + *count) belong to `rank` */
+int blinky_shard_range(int total_frames, int rank, int world, int *first, int *count);
+int blinky_shard_unique_id(unsigned char id[128]);
+/* collective: joins the group (ncclCommInitRank) */
+int blinky_shard_init(blinky_ctx *ctx, int rank, int world, const unsigned char id[128]);
+/* collective: rank 0 allocates the gather buffer (total_frames x [height][width] bytes, frame f at
+ * f*width*height) and shares it; *root_buffer is that device pointer on rank 0 and NULL elsewhere.
+ * Needs a built lensmap.  The buffer lives until the next call or blinky_shard_close. */
+int blinky_shard_buffer(blinky_ctx *ctx, int total_frames, void **root_buffer);
+/* collective: d_faces = this rank's block of frames (device memory, frame stride face_stride).
+ * Stream-ordered: the work starts after what `stream` holds and `stream` then waits for it; on rank 0
+ * the gathered batch is complete when `stream` reaches that point. */
+int blinky_shard_warp_gather(blinky_ctx *ctx, const void *d_faces, size_t face_stride, int total_frames, int mode,
+                             int chunk_frames, void *stream);
+int blinky_shard_sync(blinky_ctx *ctx);
+int blinky_shard_close(blinky_ctx *ctx);
+
 /* Fused 8-bit -> 32-bit palette expansion (engine/common/vid_sdl.c:539-546,
  * d_8to24table): same warp, output one uint32 per pixel.  table: 256 entries. */
 int blinky_set_rgba_table(blinky_ctx *ctx, const uint32_t table[256]);
@@ -251,10 +281,13 @@ int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_st
 const char *blinky_plan_summary(blinky_ctx *ctx);
 /* The tile plan the kernels read: 16-byte tile descriptors
  * {u32 entry_offset; i16 box_x, box_y; u8 plate, type (0 empty, 1 box, 2 gather, 3 box fully mapped),
- * box_w/16, box_h/8; u16 px, py} with BOX tiles first, and the entry blocks (per tile 1024 entries:
- * 16-bit {bit 15 valid, bits 12-14 tint, bits 0-11 offset inside the box} for BOX tiles, the packed
- * 32-bit lensmap format for GATHER tiles).  Pass NULL buffers to query the sizes.  Works on CPU-only
- * contexts; the tests interpret the plan on the CPU to pin this layout. */
+ * box_w/16, box_h/8; u16 px, py} — the upper six bits of `type` are the index of the box shape (one TMA
+ * descriptor per shape, at most 64) — ordered BOX tiles, GATHER tiles, EMPTY tiles, and the entry blocks in
+ * the same order, fixed sizes: BOX 3072 bytes = [4][32 lanes][8] uint16 {bit 15 valid, bits 0-13 offset
+ * inside the box} in the ring kernel's lane order (lane l, entry i -> tile row (l>>3) + 4*(i>>2), column
+ * 4*(l&7) + (i&3)) followed by [2][32 lanes][16] tint bytes (0-5 plate, 6 none); GATHER 4096 bytes =
+ * [32][32] packed 32-bit lensmap entries.  Pass NULL buffers to query the sizes.  Works on CPU-only contexts;
+ * the tests interpret the plan on the CPU to pin this layout (tests/test_tile_plan.py). */
 int blinky_get_tile_plan(blinky_ctx *ctx, void *tiles_out, size_t tiles_cap, void *entries_out, size_t entries_cap, size_t *ntiles,
                          size_t *entry_bytes);
 /* FNV-1a digest of the tile table + entry blocks planned on `threads` host threads (the plan

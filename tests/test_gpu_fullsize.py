@@ -200,7 +200,7 @@ def test_ring_pipeline_under_store_backpressure(bb, fe, palette):
                 h_out[:] = 0xEE
                 fe.warp(d_faces, int(h_out.ctypes.data), nframes=N)
                 torch.cuda.synchronize()
-                assert "tiled" in fe.last_kernel
+                assert "ring" in fe.last_kernel
                 bad = int((h_out != want).sum())
                 assert bad == 0, (lens, launch, bad)
     finally:

@@ -68,7 +68,7 @@ def test_c1_against_oracle_and_golden(bb, fe, restate, palette, torch_mod, rubix
     fe.set_background(bg)
     faces = bb.synthetic_faces(6, PS, 0)
     got = gpu_warp(torch_mod, fe, faces)[0]
-    assert ("tiled" if kernel == 0 else "gather") in fe.last_kernel
+    assert ("warp_ring_kernel" if kernel == 0 else "warp_gather_kernel") in fe.last_kernel
     om = restate.build("cube", "panini", W, H, PS, zoom=("f_fov", 180))
     idx, tint = fe.lensmap()
     assert np.array_equal(idx, om["idx"]) and np.array_equal(tint, om["tint"])

@@ -1,7 +1,8 @@
 """The tile plan is the lensmap's layout in HBM — what the warp kernels actually read.
-Here it is interpreted on the CPU, tile by tile the way the kernels do (source box cut out of the
-faces with zero fill outside the plate, 16-bit entries indexing into the box; 32-bit entries for
-gather tiles; background for empty tiles and unmapped pixels), and the result must be the reference's
+Here it is interpreted on the CPU, tile by tile the way the ring kernel does (source box cut out of the
+faces with zero fill outside the plate; 16-bit entries in the kernel's lane order indexing into the
+box, tint bytes in their own block; 32-bit entries for gather tiles; background for empty tiles and
+unmapped pixels; entry blocks addressed by tile index alone), and the result must be the reference's
 render_lensmap.  This pins the planner and the layout contract without a GPU."""
 import numpy as np
 import pytest
@@ -9,45 +10,68 @@ import pytest
 EMPTY, BOX, GATHER, BOX_FULL = 0, 1, 2, 3
 
 
-def render_from_plan(fe, faces, palmaps, bg, rubix):
+BOX_BLOCK, GATHER_BLOCK = 2048 + 1024, 4096
+
+
+def lane_pixel(lane, i):
+    """pixel i (0..31) of lane `lane` in a BOX tile: 8 quads of 4 consecutive pixels, 4 rows apart"""
+    return (lane >> 3) + 4 * (i >> 2), 4 * (lane & 7) + (i & 3)
+
+
+def render_from_plan(fe, faces, palmaps, bg, rubix, max_box=8192):
     tiles, entries = fe.tile_plan()
     W, H, ps, P = fe.width, fe.height, fe.platesize, fe.numplates
     faces = faces.reshape(P, ps, ps)
     out = bg.copy()
     covered = np.zeros((H, W), bool)
-    lut = np.concatenate([palmaps, np.arange(256, dtype=np.uint8)[None]] * 1 + [np.arange(256, dtype=np.uint8)[None]])  # tint 6/7 -> identity
-    seen_non_box = False
-    for t in tiles:
+    lut = np.concatenate([palmaps, np.arange(256, dtype=np.uint8)[None], np.arange(256, dtype=np.uint8)[None]])  # tint 6/7 -> identity
+    types = tiles["type"] & 3
+    is_box = np.isin(types, (BOX, BOX_FULL))
+    nbox, ngather = int(is_box.sum()), int((types == GATHER).sum())
+    # class order: BOX*, GATHER*, EMPTY* — block addresses then follow from the index alone
+    assert is_box[:nbox].all() and (types[nbox:nbox + ngather] == GATHER).all() and (types[nbox + ngather:] == EMPTY).all()
+    assert entries.size >= nbox * BOX_BLOCK + ngather * GATHER_BLOCK
+    lanes = np.arange(32)
+    shapes = {}
+    for n, t in enumerate(tiles):
         x0, y0 = int(t["px"]), int(t["py"])
         assert x0 % 32 == 0 and y0 % 32 == 0 and x0 < W and y0 < H
         ys, xs = min(32, H - y0), min(32, W - x0)
         assert not covered[y0:y0 + ys, x0:x0 + xs].any(), "tiles overlap"
         covered[y0:y0 + ys, x0:x0 + xs] = True
-        ty = int(t["type"])
+        ty = int(t["type"]) & 3          # upper six bits: index of the box shape (one TMA descriptor per shape)
         if ty in (BOX, BOX_FULL):
-            assert not seen_non_box, "BOX tiles must come first (the ring kernel walks [0, n_box))"
+            shape = int(t["type"]) >> 2
+            shapes.setdefault(shape, (int(t["box_w16"]), int(t["box_h8"])))
+            assert shapes[shape] == (int(t["box_w16"]), int(t["box_h8"])) and shape < 64
             bw, bh = int(t["box_w16"]) * 16, int(t["box_h8"]) * 8
             bx, by, plate = int(t["box_x"]), int(t["box_y"]), int(t["plate"])
-            assert 16 <= bw <= 128 and 8 <= bh <= 256 and bw * bh <= 4096 and bx % 16 == 0  # TMA constraints
-            assert int(t["entry_offset"]) % 16 == 0
+            assert 16 <= bw <= 256 and 8 <= bh <= 256 and bw * bh <= max_box and bx % 16 == 0  # TMA constraints
+            assert int(t["entry_offset"]) == n * BOX_BLOCK
             box = np.zeros((bh, bw), np.uint8)  # TMA zero-fills what lies outside the tensor
             sy0, sy1 = max(by, 0), min(by + bh, ps)
             sx0, sx1 = max(bx, 0), min(bx + bw, ps)
             if sy1 > sy0 and sx1 > sx0:
                 box[sy0 - by:sy1 - by, sx0 - bx:sx1 - bx] = faces[plate, sy0:sy1, sx0:sx1]
-            e = entries[int(t["entry_offset"]):int(t["entry_offset"]) + 2048].view("<u2").reshape(32, 32)
+            blk = entries[n * BOX_BLOCK:(n + 1) * BOX_BLOCK]
+            ent = blk[:2048].view("<u2").reshape(4, 32, 8)     # [load k][lane][j]: pixel i = 8k + j
+            tnt = blk[2048:].reshape(2, 32, 16)                # [m][lane][j]: pixel i = 16m + j
+            e = np.zeros((32, 32), np.uint16)
+            tint = np.zeros((32, 32), np.int64)
+            for i in range(32):
+                r, c = lane_pixel(lanes, i)
+                e[r, c] = ent[i >> 3, lanes, i & 7]
+                tint[r, c] = tnt[i >> 4, lanes, i & 15]
             valid = (e & 0x8000) != 0
             if ty == BOX_FULL:
                 assert valid.all() and ys == 32 and xs == 32
-            off = (e & 0x0FFF).astype(np.int64)
-            assert (off[valid] < bw * bh).all()
+            off = (e & 0x3FFF).astype(np.int64)
+            assert (off[valid] < bw * bh).all() and (tint <= 6).all() and (tint[~valid] == 6).all()
             px = box.reshape(-1)[np.where(valid, off, 0)]
-            tint = ((e >> 12) & 7).astype(np.int64)
         else:
-            seen_non_box = True
             if ty == EMPTY:
                 continue
-            assert ty == GATHER and int(t["entry_offset"]) % 16 == 0
+            assert ty == GATHER and int(t["entry_offset"]) == nbox * BOX_BLOCK + (n - nbox) * GATHER_BLOCK
             e = entries[int(t["entry_offset"]):int(t["entry_offset"]) + 4096].view("<u4").reshape(32, 32)
             valid = (e & 0x80000000) != 0
             px = faces.reshape(-1)[np.where(valid, e & 0x0FFFFFFF, 0).astype(np.int64)]
@@ -90,6 +114,6 @@ def test_plan_interpreted_on_the_cpu_equals_reference_render(bb, host, restate, 
     assert np.array_equal(got, want), (globe, lens, int((got != want).sum()))
     tiles, _ = host.tile_plan()
     if ps % 16:
-        assert not np.isin(tiles["type"], (BOX, BOX_FULL)).any()
+        assert not np.isin(tiles["type"] & 3, (BOX, BOX_FULL)).any()
     elif lens == "panini":
-        assert np.isin(tiles["type"], (BOX, BOX_FULL)).mean() > 0.7  # the point of the layout
+        assert np.isin(tiles["type"] & 3, (BOX, BOX_FULL)).mean() > 0.7  # the point of the layout
