@@ -236,6 +236,80 @@ def claim_stdout():
     return real
 
 
+def setup_workload(fe, name):
+    W, H, PS, globe, lens, zoom, rubix = WORKLOADS[name]
+    for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
+        fe.command(c)
+    fe.set_rubix(rubix)
+    t0 = time.time()
+    fe.build_lensmap(W, H, PS, threads=0)  # GPU build (translated lens); every rank rebuilds deterministically: nothing to broadcast
+    return time.time() - t0
+
+
+def compulsory_bytes(fe, frames):
+    """Bytes a launch cannot avoid moving through HBM: every 32-byte sector of the faces the lensmap reads
+    (once per frame), the output (once per frame) and the tile plan's entry blocks + descriptors (once per
+    launch: they stay in L2 across the frames of a batch)."""
+    idx, _ = fe.lensmap()
+    v = idx[idx >= 0].astype(np.int64)
+    sectors = np.unique(v >> 5).size
+    tiles, entries = fe.tile_plan()
+    per_frame = sectors * 32 + fe.width * fe.height
+    return int(per_frame * frames + entries.size + tiles.nbytes), int(sectors * 32)
+
+
+def time_device(torch, fe, d_faces, d_out, frames, steps, warmup, stream, flush=None):
+    """CUDA-event time of `steps` launches (seconds per launch); flush = a >L2 buffer rewritten before every
+    launch (cold single-frame case) — then each launch is timed on its own"""
+    for _ in range(warmup):
+        fe.warp(d_faces, d_out, nframes=frames, stream=stream)
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fe.warp(d_faces, d_out, nframes=frames, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / steps
+    ts = []
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fe.warp(d_faces, d_out, nframes=frames, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return float(np.median(ts))
+
+
+def roofline_entry(fe, launch_s, frames, peak, traffic):
+    npix, M = fe.width * fe.height, fe.mapped_pixels
+    alg = (5 * npix + M) * frames  # SURVEY section 8d: 4 B lensmap entry + 1 B source (mapped) + 1 B output per pixel
+    comp, face_sector_bytes = compulsory_bytes(fe, frames)
+    out = {"achieved": round(alg / launch_s / 1e9, 1), "frac": round(alg / launch_s / 1e9 / peak, 4),
+           "algorithmic_bytes_per_launch": int(alg), "launch_us": round(launch_s * 1e6, 2),
+           "compulsory_bytes_per_launch": comp, "compulsory_frac": round(comp / launch_s / 1e9 / peak, 4),
+           "face_sector_bytes_per_frame": face_sector_bytes}
+    if traffic:
+        out["traffic"] = traffic
+        out["dram_frac"] = round(traffic["dram_bytes_per_launch"] / launch_s / 1e9 / peak, 4)
+    else:
+        out["traffic"] = None
+        out["dram_frac"] = None
+    return out
+
+
+def load_traffic():
+    """measured DRAM bytes per launch (ncu, this round) per workload: profiles/traffic_r2.json, written by
+    scripts/ncu_traffic.py from the committed .ncu-rep summaries"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
 def main():
     global OUT
     OUT = claim_stdout()
@@ -246,8 +320,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k-cube-panini", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=16, help="distinct frames per GPU per step")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto (tiled TMA), 1 flat gather")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (ring kernel, TMA-staged boxes), 1 flat gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--gather-mode", default="nccl", choices=["nccl", "peer_copy", "peer_store"])
+    ap.add_argument("--chunk", type=int, default=4, help="frames per gather chunk (N > 1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -260,6 +337,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
 
@@ -270,25 +348,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from blinky_b200.sharding import frames_for_rank, gather_frames
 
     W, H, PS, globe, lens, zoom, rubix = WORKLOADS[args.workload]
     F = args.frames
     fe = bb.Fisheye(device=local_rank, palette=bb.synthetic_palette())
-    for c in (f"f_globe {globe}", f"f_lens {lens}", zoom):
-        fe.command(c)
-    fe.set_rubix(rubix)
-    t0 = time.time()
-    fe.build_lensmap(W, H, PS, threads=0)  # GPU build (translated lens); every rank rebuilds deterministically: nothing to broadcast
-    build_s = time.time() - t0
+    build_s = setup_workload(fe, args.workload)
     build_info = fe.build_info
     fe.set_kernel(args.kernel)
     P, M, npix = fe.numplates, fe.mapped_pixels, W * H
-    my_frames = frames_for_rank(F * world, rank, world)  # global frame ids of this rank's batch
     gen = torch.Generator(device="cuda").manual_seed(1000 + rank)
     d_faces = torch.randint(0, 256, (F, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
     d_out = torch.zeros((F, H, W), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = hbm_peak()
+    traffic_db = load_traffic()
 
     def barrier():
         if world > 1:
@@ -298,6 +371,13 @@ def main():
     def step():
         fe.warp(d_faces, d_out, nframes=F, stream=stream)
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident warp: every rank its own batch, nothing exchanged ---------------------
     for _ in range(args.warmup):
         step()
     barrier()
@@ -312,7 +392,8 @@ def main():
     e1.record()
     barrier()
     launches = fe.launch_count - launches0
-    elapsed = e0.elapsed_time(e1) * 1e-3
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    kernel_name = fe.last_kernel
     # the timed region is a few milliseconds: keep the identical load running so that NVML
     # (which refreshes every few ms) actually sees the clocks this kernel runs at
     t_end = time.time() + 1.0
@@ -321,13 +402,9 @@ def main():
             step()
         torch.cuda.synchronize()
     sampler.stop()
-    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
-    value = world * F * args.steps * npix / elapsed / 1e6
+    warp_value = world * F * args.steps * npix / elapsed / 1e6
 
-    # ---- end to end through the C ABI's host entry point ---------------------------------
+    # ---- end to end through the C ABI's host entry point ------------------------------------------
     h_faces = fe.alloc_pinned(F * P * PS * PS)
     h_out = fe.alloc_pinned(F * npix)
     h_faces[:] = d_faces.cpu().numpy().reshape(-1)
@@ -338,135 +415,57 @@ def main():
     for _ in range(e2e_steps):
         fe.warp_host(h_faces, h_out.reshape(F, H, W))
     torch.cuda.synchronize()
-    e2e_t = time.perf_counter() - t0
+    e2e_t = max_over_ranks(time.perf_counter() - t0)
     same = bool(np.array_equal(h_out.reshape(F, H, W)[F - 1], d_out[F - 1].cpu().numpy()))
-    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * e2e_steps * npix / float(te.item()) / 1e6
+    e2e_value = world * F * e2e_steps * npix / e2e_t / 1e6
+    upload_bytes = int(fe.upload_bytes_per_frame * F)
     fe.free_pinned(h_faces)
     fe.free_pinned(h_out)
 
-    # ---- the final gather to rank 0 (reference topology), timed on its own ---------------
+    # ---- N > 1: the reference topology — finished frames reach rank 0 (C ABI: blinky_shard_*) --------
     gather = None
+    value = warp_value
     if world > 1:
-        gathered = gather_frames(d_out, rank, world)  # untimed: NCCL sets its p2p connections up lazily
-        barrier()
-        reps = 5
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(reps):
-            gathered = gather_frames(d_out, rank, world)
-        g1.record()
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1) * 1e-3 / reps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gsec = float(tg.item())
-        gather = {"ms": round(gsec * 1e3, 3), "bytes_into_rank0": (world - 1) * F * npix,
-                  "GBs_into_rank0": round((world - 1) * F * npix / gsec / 1e9, 1), "included_in_value": False,
-                  "value_with_gather": round(world * F * npix / (elapsed / args.steps + gsec) / 1e6, 1),
-                  "how": "torch.distributed (NCCL) send/recv of each rank's finished uint8 frames to rank 0"}
-        if rank == 0:
-            assert gathered.shape[0] == world * F
-        # -- fused: every rank's warp kernel stores straight into rank 0's buffer (peer memory over NVLink)
-        frame_bytes = npix
-        base = fe.alloc_device(world * F * frame_bytes) if rank == 0 else 0
-        handle = [fe.ipc_export(base) if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        peer = base if rank == 0 else fe.ipc_open(handle[0])
-        mine = peer + rank * F * frame_bytes
-        if rank == 0:  # poison: a store that never lands shows up as 0xEE
-            class _Raw0:
-                __cuda_array_interface__ = {"shape": (world * F * frame_bytes,), "typestr": "|u1", "data": (base, False), "version": 2}
-
-            torch.as_tensor(_Raw0(), device="cuda").fill_(0xEE)
-        barrier()
-        for _ in range(3):
-            fe.warp(d_faces, mine, nframes=F, stream=stream)
-        barrier()
-        fsteps = max(5, min(args.steps, 20))
-        f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0e.record()
-        for _ in range(fsteps):
-            fe.warp(d_faces, mine, nframes=F, stream=stream)
-        f1e.record()
-        barrier()
-        tf = torch.tensor([f0e.elapsed_time(f1e) * 1e-3 / fsteps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        fsec = float(tf.item())
-        fused_ok = None
-        if rank == 0:
-            # view rank 0's raw gather buffer as a tensor and compare with the NCCL-gathered frames
-            class _Raw:
-                __cuda_array_interface__ = {"shape": (world * F, H, W), "typestr": "|u1", "data": (base, False), "version": 2}
-
-            fused_buf = torch.as_tensor(_Raw(), device="cuda")
-            fused_ok = bool(torch.equal(fused_buf, gathered))
-            if not fused_ok:  # say where, and who is right: recompute the frames here with the flat kernel
-                for r in range(world):
-                    a, b = fused_buf[r * F:(r + 1) * F].reshape(-1), gathered[r * F:(r + 1) * F].reshape(-1)
-                    bad = (a != b).nonzero().flatten()
-                    if bad.numel():
-                        gen_r = torch.Generator(device="cuda").manual_seed(1000 + r)
-                        faces_r = torch.randint(0, 256, (F, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen_r)
-                        truth = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
-                        fe.set_kernel(1)
-                        fe.warp(faces_r, truth, nframes=F, stream=stream)
-                        torch.cuda.synchronize()
-                        fe.set_kernel(args.kernel)
-                        t = truth.reshape(-1)
-                        k = int(bad[0])
-                        print(f"[bench] fused != nccl for rank {r}: {bad.numel()} bytes, first at frame {k // npix} pixel {k % npix}: "
-                              f"fused {a[k:k + 4].tolist()} nccl {b[k:k + 4].tolist()} flat-kernel truth {t[k:k + 4].tolist()}; "
-                              f"fused wrong bytes {int((a != t).sum())}, nccl wrong bytes {int((b != t).sum())}", file=sys.stderr)
-        gather.update({"fused_ms_per_step": round(fsec * 1e3, 3), "fused_value": round(world * F * npix / fsec / 1e6, 1),
-                       "fused_matches_nccl_gather": fused_ok,
-                       "fused_how": "warp kernels write their finished frames directly into rank 0's buffer through CUDA-IPC peer "
-                                    "memory (NVLink stores from inside the kernel); no separate collective"})
-        barrier()
-        if rank != 0:
-            fe.ipc_close(peer)
-        barrier()
-        if rank == 0:
-            fe.free_device(base)
+        gather = run_sharded(args, torch, dist, bb, fe, d_faces, rank, world, barrier, max_over_ranks, stream)
+        value = gather["value"]
 
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        alg_bytes = (5 * npix + M) * F  # 4 B lensmap entry + 1 B source (mapped) + 1 B output per pixel
-        # a step is one launch of K2, plus one of K3 when the plan was split: the roofline is
-        # taken over the whole step (all kernels that together warp the batch)
         launch_s = elapsed / args.steps
-        achieved = alg_bytes / launch_s / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        except Exception:  # noqa: BLE001
-            pass
+        roof = roofline_entry(fe, launch_s, F, peak, traffic_db.get(args.workload))
+        roof.update({"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                     "kernels_per_step": int(launches // max(1, args.steps)),
+                     "note": "frac = SURVEY 8(d) algorithmic bytes (5*W*H + M per frame) / CUDA-event launch time / peak; "
+                             "compulsory_frac = bytes the launch cannot avoid (sampled 32-byte face sectors + output per frame, "
+                             "tile plan once per launch) / time / peak — computed in this run; dram_frac = DRAM bytes per launch "
+                             "measured by ncu this round (profiles/traffic_r2.json) / this run's launch time / peak"})
         line = {
             "metric": "lens-warp Mpixels/s", "value": round(value, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(elapsed / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "screen": [W, H], "globe": globe, "numplates": P, "platesize": PS, "lens": lens,
                        "zoom": zoom, "rubix": rubix, "frames_per_gpu_per_step": F, "global_batch_frames": F * world,
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"
+                                      + ("; finished frames gathered on rank 0 (value = delivered rate)" if world > 1 else ""),
                        "l2": "inputs larger than L2 (403 MB of distinct faces per step); lensmap reused across frames by design",
                        "mapped_pixel_fraction": round(M / npix, 4), "lensmap_build_s": round(build_s, 3), "lensmap_build": build_info,
                        "tiling": fe.plan_summary},
-            "kernel": fe.last_kernel, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "launch_us": round(launch_s * 1e6, 2),
-                         "kernels_per_step": int(launches // max(1, args.steps)),
-                         "note": "achieved = (5*W*H + M) bytes/frame x frames per step / CUDA-event time of the step "
-                                 "(K2 tiled kernel, plus K3 gather kernel when the tile plan is split)"},
-            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": int(fe.upload_bytes_per_frame * F),
+            "kernel": kernel_name, "gpu_launches": int(launches),
+            "value_warp_only": round(warp_value, 1),
+            "roofline": roof,
+            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": upload_bytes,
                     "d2h_bytes_per_step": int(npix * F), "steps": e2e_steps, "matches_device_path": same,
-                    "how": "blinky_warp_host: pinned host faces -> cudaMemcpy2DAsync (per shown plate, only the texel rectangle the lens samples) -> kernel -> "
-                           "cudaMemcpy2DAsync back, 3-slot stream pipeline; wall clock around synchronous calls"},
+                    "how": "blinky_warp_host: pinned host faces -> async copies of the texel rectangle each shown plate is sampled in -> "
+                           "kernel -> copy back, multi-slot stream pipeline; wall clock around synchronous calls"},
             "clocks": sampler.summary("sampled by NVML over the timed region plus 1 s of the identical load"),
         }
         if gather:
             line["gather"] = gather
+    # ---- the other BASELINE configurations (device-resident; every rank runs them, rank 0 reports) ----
+    if world == 1 and not args.no_secondary:
+        secondary = run_secondary(args, torch, bb, fe, peak, traffic_db, stream)
+        if rank == 0:
+            line["secondary"] = secondary
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(WORKLOADS[args.workload])
         print(json.dumps(line), file=OUT, flush=True)
@@ -474,6 +473,141 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: keep the process (and therefore its pinned allocations, first-touch) on the
+    NUMA node its GPU hangs off, so that 8 ranks do not push their PCIe traffic through one socket."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        node = None
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:  # noqa: BLE001
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read())
+        if node is None or node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def run_sharded(args, torch, dist, bb, fe, d_faces, rank, world, barrier, max_over_ranks, stream):
+    """N > 1: blinky_shard_warp_gather — every rank warps its block of the global batch, finished frames
+    are gathered on rank 0 chunk by chunk, overlapped with the warp of the next chunk.  All three
+    transports are timed; `value` is the one asked for with --gather-mode (default NCCL, the north-star's)."""
+    from oracle.pyoracle import Restatement
+
+    F = d_faces.shape[0]
+    W, H = fe.width, fe.height
+    npix = W * H
+    total = F * world
+    uid = [bb.shard_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    fe.shard_init(rank, world, uid[0])
+    root = fe.shard_buffer(total)
+    modes = {"nccl": bb.GATHER_NCCL, "peer_copy": bb.GATHER_PEER_COPY, "peer_store": bb.GATHER_PEER_STORE}
+    out = {"chunk_frames": args.chunk, "bytes_into_rank0_per_step": (world - 1) * F * npix, "modes": {}}
+    gathered = None
+    if rank == 0:
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (total, H, W), "typestr": "|u1", "data": (root, False), "version": 2}
+
+        gathered = torch.as_tensor(_Raw(), device="cuda")
+    reference = None
+    for name, mode in modes.items():
+        if rank == 0:
+            gathered.fill_(0xEE)  # a frame that never lands shows up
+        barrier()
+        for _ in range(3):
+            fe.shard_warp_gather(d_faces, total, mode, args.chunk, stream=stream)
+        barrier()
+        steps = max(5, min(args.steps, 20))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            fe.shard_warp_gather(d_faces, total, mode, args.chunk, stream=stream)
+        g1.record()
+        barrier()
+        sec = max_over_ranks(g0.elapsed_time(g1) * 1e-3 / steps)
+        entry = {"ms_per_step": round(sec * 1e3, 4), "value": round(total * npix / sec / 1e6, 1),
+                 "GBs_into_rank0": round((world - 1) * F * npix / sec / 1e9, 1)}
+        if rank == 0:
+            if reference is None:
+                reference = gathered.clone()
+                entry["bytes_equal_first_mode"] = True
+            else:
+                entry["bytes_equal_first_mode"] = bool(torch.equal(gathered, reference))
+        out["modes"][name] = entry
+    # one gathered frame per rank against the oracle (restated render_lensmap on the product's lensmap,
+    # which the GPU suite compares with the oracle's own build)
+    if rank == 0:
+        orc = Restatement()
+        idx, tint = fe.lensmap()
+        pm = orc.palmaps(bb.synthetic_palette())
+        checked = []
+        for r in range(world):
+            gen_r = torch.Generator(device="cuda").manual_seed(1000 + r)
+            faces_r = torch.randint(0, 256, tuple(d_faces.shape), dtype=torch.uint8, device="cuda", generator=gen_r)
+            k = (r * 7 + 3) % F
+            want = orc.render(idx, tint, faces_r[k].cpu().numpy(), pm, fe.rubix_enabled, background=np.zeros((H, W), np.uint8),
+                              threads=bb.usable_cpus())
+            got = reference[r * F + k].cpu().numpy()
+            checked.append(bool(np.array_equal(got, want)))
+        out["oracle_check"] = {"frames_checked": world, "all_equal": all(checked),
+                               "how": "one gathered frame per rank vs oracle.render (restated render_lensmap, engine/NQ/fisheye.c:2406-2424)"}
+        if not all(checked):
+            print(f"[bench] gathered frames differ from the oracle: {checked}", file=sys.stderr)
+    chosen = out["modes"][args.gather_mode]
+    out.update({"mode": args.gather_mode, "ms": chosen["ms_per_step"], "value": chosen["value"], "included_in_value": True,
+                "how": "blinky_shard_warp_gather (C ABI): per rank a compute stream warps chunk k+1 while a communication stream moves "
+                       "chunk k to rank 0 (ncclSend/ncclRecv, copy-engine peer copies, or in-kernel peer stores)"})
+    fe.shard_close()
+    return out
+
+
+SECONDARY = ["1080p-cube-panini170", "4k-cube-quincuncial-rubix", "4k-cube-stereographic", "4k-cube-equirect", "4k-cube-hammer",
+             "4k-cube-fisheye1", "4k-trism-stereographic"]
+
+
+def run_secondary(args, torch, bb, fe, peak, traffic_db, stream):
+    """every other BASELINE configuration, device-resident: batched launch (16 frames) and a single cold frame
+    (L2 flushed before each launch — the in-engine shape), both fractions of the HBM roofline"""
+    rows = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    names = [args.workload] + [n for n in SECONDARY if n != args.workload]
+    for name in names:
+        W, H, PS = WORKLOADS[name][:3]
+        F = args.frames
+        build_s = setup_workload(fe, name)
+        P = fe.numplates
+        gen = torch.Generator(device="cuda").manual_seed(2000)
+        d_faces = torch.randint(0, 256, (F, P, PS, PS), dtype=torch.uint8, device="cuda", generator=gen)
+        d_out = torch.zeros((F, H, W), dtype=torch.uint8, device="cuda")
+        row = {"workload": name, "lensmap_build_s": round(build_s, 3), "tiling": fe.plan_summary, "frames_per_launch": F}
+        if name != args.workload:
+            t = time_device(torch, fe, d_faces, d_out, F, 10, 3, stream)
+            row.update({"us_per_frame": round(t * 1e6 / F, 2), "value": round(W * H * F / t / 1e6, 1), "kernel": fe.last_kernel,
+                        "roofline": roofline_entry(fe, t, F, peak, traffic_db.get(name))})
+        tc = time_device(torch, fe, d_faces, d_out, 1, 7, 3, stream, flush=flush)
+        row["single_frame_cold"] = {"us": round(tc * 1e6, 2), "value": round(W * H / tc / 1e6, 1),
+                                    "roofline": roofline_entry(fe, tc, 1, peak, None)}
+        rows.append(row)
+        del d_faces, d_out
+    return rows
 
 
 if __name__ == "__main__":

@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // pixels of one row.  EMPTY tiles copy the background.
 // --------------------------------------------------------------------------
 constexpr int kRingMaxStages = 4;
-constexpr int kStaticTickets = 3;  // units a warp owns before it draws from the counter
 
 struct RingParams {
     const TileDesc *tiles;
@@ -200,14 +199,12 @@ struct RingParams {
     size_t out_stride;
     uint32_t *ticket;       // monotonic counter (never reset: see launch_ring)
     uint32_t ticket_base;   // its value when this launch starts
+    uint32_t nstatic;       // units per warp that are assigned statically (warp w owns w, w+NW, ...) before it draws tickets
     uint32_t nbox, ngather, ntiles;
     uint32_t nframes, fchunk, nchunks, nunits;
     uint32_t stage_bytes, nstages;
     int width, height;
     uint32_t zero;  // always 0, but only the host knows: see stage_dep()
-    uint32_t lab;   // BLINKY_LAB experiment bits (0 in production): 1 no LDS, 2 no TMA, 4 no stores
-    uint32_t prefetch;  // L2 prefetch distance in boxes ahead of the TMA issue (0 = off)
-    int platesize;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -277,15 +274,39 @@ struct RingTmaps {
 struct RingUnit {     // what the warp knows about one of its upcoming units (all warp-uniform)
     uint32_t ticket;  // unit index; >= nunits: none
     uint32_t tile, f0, nf;
-    uint32_t dy, dz, dw;  // TileDesc words 1..3: box origin | plate, type/shape, box shape | tile origin
+    uint32_t type;    // TileType
+    uint32_t dw;      // tile origin on the screen (x | y << 16)
+    // BOX units: everything a TMA issue needs, worked out once per unit
+    uint64_t tmap;    // generic address of the shape's descriptor in the parameter block
+    int bx, by, plate;
+    uint32_t bytes;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// eight 32-bit streaming stores in ONE asm statement: all eight addresses are live at once, so the
+// stores issue back to back (with one store per statement the compiler recycled a single address
+// register pair and every store waited for the previous one to read its operands)
+__device__ __forceinline__ void st_stream_u32x8(const uint64_t (&a)[8], const uint32_t (&w)[8]) {
+    asm volatile(
+        "st.global.cs.u32 [%0], %8;\n\t"
+        "st.global.cs.u32 [%1], %9;\n\t"
+        "st.global.cs.u32 [%2], %10;\n\t"
+        "st.global.cs.u32 [%3], %11;\n\t"
+        "st.global.cs.u32 [%4], %12;\n\t"
+        "st.global.cs.u32 [%5], %13;\n\t"
+        "st.global.cs.u32 [%6], %14;\n\t"
+        "st.global.cs.u32 [%7], %15;"
+        ::"l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7]),
+          "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+        : "memory");
+}
 
-template <bool RUBIX, bool RGBA>
-__global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant__ RingParams p, const __grid_constant__ RingTmaps tm) {
+// MINB: warps (= CTAs) per SM the register allocation is sized for
+template <bool RUBIX, bool RGBA, int MINB>
+__global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_constant__ RingParams p, const __grid_constant__ RingTmaps tm) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t lane = threadIdx.x;
+    // XOR with a parameter that is always zero: keeps ptxas from re-reading the special register
+    // (S2R, tens of cycles) at every `lane == 0` test instead of holding the lane number in a register
+    const uint32_t lane = threadIdx.x ^ p.zero;
     const uint32_t S = p.stage_bytes, D = p.nstages;
     const uint32_t ring = smem_u32(smem_raw);
     uint8_t *tail = smem_raw + static_cast<size_t>(S) * D;
@@ -314,15 +335,21 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
     auto describe = [&](uint32_t ticket) {
         RingUnit u;
         u.ticket = ticket;
-        u.tile = 0; u.f0 = 0; u.nf = 0;
-        u.dy = u.dz = u.dw = 0;
+        u.tile = 0; u.f0 = 0; u.nf = 0; u.type = TILE_EMPTY; u.dw = 0;
+        u.tmap = 0; u.bx = u.by = u.plate = 0; u.bytes = 0;
         if (ticket < p.nunits) {
             u.tile = ticket / p.nchunks;
             const uint32_t chunk = ticket - u.tile * p.nchunks;
             u.f0 = chunk * p.fchunk;
             u.nf = min(p.fchunk, p.nframes - u.f0);
             const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + u.tile));
-            u.dy = d.y; u.dz = d.z; u.dw = d.w;
+            u.type = (d.z >> 8) & kTileTypeMask;
+            u.dw = d.w;
+            u.tmap = reinterpret_cast<uint64_t>(&tm.m[(d.z >> (8 + kTileShapeShift)) & 63u]);
+            u.bx = static_cast<int16_t>(d.y & 0xffffu);
+            u.by = static_cast<int16_t>(d.y >> 16);
+            u.plate = static_cast<int>(d.z & 0xffu);
+            u.bytes = ((d.z >> 16) & 0xffu) * (d.z >> 24) * 128u;
         }
         return u;
     };
@@ -340,56 +367,44 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
         }
     };
 
-    // ring state (warp-uniform)
-    uint32_t cs = 0, is = 0, phases = 0, inflight = 0;
-    auto issue_box = [&](uint32_t dy, uint32_t dz, uint32_t frame, uint32_t dep) {
-        if (lane == 0) {
-            const uint32_t w16 = (dz >> 16) & 0xffu, h8 = dz >> 24, shape = (dz >> (8 + kTileShapeShift)) & 63u;
-            const uint32_t bar = bars + 8 * is;
-            if (p.lab & 2u) {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-            } else {
-                mbar_expect_tx(bar, w16 * 16u * h8 * 8u);
-                tma_load_box(ring + is * S + dep, &tm.m[shape], static_cast<int>(static_cast<int16_t>(dy & 0xffffu)),
-                             static_cast<int>(static_cast<int16_t>(dy >> 16)), static_cast<int>(dz & 0xffu), static_cast<int>(frame), bar);
-            }
+    // Work distribution: the first `nstatic` units of a warp are fixed (w, w + NW, ...), the rest of the
+    // launch is handed out through the ticket counter.  Mostly static because one counter serves the
+    // whole GPU and same-address atomics serialise; the dynamic tail evens out the finish.
+    // A warp draws only while its last known ticket was good, so that the number of draws per launch is
+    // a function of the launch alone (the host advances ticket_base by it).
+    uint32_t k_next = 0;        // index of the next ticket of this warp
+    bool last_good = true;
+    auto draw_now = [&]() {     // the k_next-th ticket, waiting for the counter if it is a dynamic one
+        uint32_t t = 0xffffffffu;
+        if (k_next < p.nstatic) {
+            t = blockIdx.x + k_next * NW;
+        } else if (last_good) {
+            uint32_t d = 0;
+            if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(d) : "l"(p.ticket) : "memory");
+            t = p.nstatic * NW + (__shfl_sync(0xffffffffu, d, 0) - p.ticket_base);
         }
-        is = is + 1 == D ? 0 : is + 1;
-        ++inflight;
+        ++k_next;
+        last_good = t < p.nunits;
+        return t;
     };
-    // L2 prefetch of a box some frames before its TMA load is issued: the TMA unit keeps a bounded number
-    // of row requests in flight, so what it can stream is (requests in flight) / latency — rows that
-    // already sit in L2 return three times sooner than rows that come from HBM (scripts/tma_lab.cu).
-    // One `prefetch.global.L2` per 128-byte line of each box row, rows spread over the lanes.
-    auto prefetch_box = [&](uint32_t dy, uint32_t dz, uint32_t frame) {
-        const int x = static_cast<int16_t>(dy & 0xffffu), y = static_cast<int16_t>(dy >> 16);
-        const int w = static_cast<int>((dz >> 16) & 0xffu) * 16, h = static_cast<int>(dz >> 24) * 8, ps = p.platesize;
-        const uint8_t *base = p.faces + static_cast<size_t>(frame) * p.face_stride + static_cast<size_t>(dz & 0xffu) * ps * ps;
-        const int x1 = min(x + w, ps) - 1;
-        for (int r = static_cast<int>(lane); r < h; r += 32) {
-            const int yy = y + r;
-            if (yy < 0 || yy >= ps) continue;
-            const uint8_t *row = base + static_cast<size_t>(yy) * ps;
-            for (int c = x & ~127; c <= x1; c += 128) prefetch_l2(row + max(c, x));
-        }
-    };
-
-    RingUnit A = describe(blockIdx.x), B = describe(blockIdx.x + NW), C = describe(blockIdx.x + 2 * NW);
+    RingUnit A = describe(draw_now());
+    RingUnit B = describe(draw_now());
+    RingUnit C = describe(draw_now());
     uint4 eA[4], tA[2], eB[4], tB[2];
     load_box_entries(A, eA, tA);
-    uint32_t issA = 0, issB = 0;  // boxes already issued for A / B
-    uint32_t pfA = 0, pfB = 0;    // boxes already prefetched into L2 for A / B
-    const uint32_t PF = p.prefetch;
+
+    // ring state (warp-uniform): consume stage, issue stage, phase bit per stage, boxes in flight
+    uint32_t cs = 0, is = 0, phases = 0, inflight = 0;
+    uint32_t issA = 0, issB = 0, issC = 0;  // boxes already issued for A / B / C
 
     while (A.ticket < p.nunits) {
-        // look ahead: next ticket (drawn only while the last known one was good, so that the number of
-        // draws per launch is a function of the launch alone), B's entries.  asm volatile keeps the draw
-        // HERE, a whole unit before its result is needed.
-        uint32_t drawn = 0xffffffffu - kStaticTickets * NW + p.ticket_base;  // -> next_ticket 0xffffffff when nothing is drawn
-        if (C.ticket < p.nunits && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(drawn) : "l"(p.ticket) : "memory");
+        // look ahead: next ticket, B's entries.  asm volatile keeps a dynamic draw HERE, a whole unit
+        // before its result is needed.
+        const bool draw_dynamic = k_next >= p.nstatic && last_good;
+        uint32_t drawn = 0;
+        if (draw_dynamic && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(drawn) : "l"(p.ticket) : "memory");
         load_box_entries(B, eB, tB);
 
-        const uint32_t type = (A.dz >> 8) & kTileTypeMask;
         const uint32_t tile_x = A.dw & 0xffffu, tile_y = A.dw >> 16;
         if (A.tile < p.nbox) {
             // ---- unpack the lane's 32 entries once for all frames of the unit
@@ -403,19 +418,87 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
                     off[8 * k + 2 * j + 1] = (w4[j] >> 16) & kBoxOffsetMask;
                 }
             }
-            const bool full = type == TILE_BOX_FULL;
-            const bool b_box = is_box(B);
+            const bool b_box = is_box(B), c_box = b_box && is_box(C);
+            // The next box of the warp's sequence goes into the free stage: this unit's next frame, else
+            // the first frames of the next units (while those are BOX units; short units — single-frame
+            // launches — need the look-ahead to reach two units on).  One issue site, operands selected.
+            auto advance = [&](uint32_t dep) {
+                const bool fromA = issA < A.nf;
+                const bool fromB = !fromA && b_box && issB < B.nf;
+                const bool fromC = !fromA && !fromB && c_box && issB >= B.nf && issC < C.nf;
+                if (!fromA && !fromB && !fromC) return;
+                const uint64_t tmap = fromA ? A.tmap : fromB ? B.tmap : C.tmap;
+                const int bx = fromA ? A.bx : fromB ? B.bx : C.bx, by = fromA ? A.by : fromB ? B.by : C.by;
+                const int plate = fromA ? A.plate : fromB ? B.plate : C.plate;
+                const uint32_t bytes = fromA ? A.bytes : fromB ? B.bytes : C.bytes;
+                const uint32_t frame = fromA ? A.f0 + issA : fromB ? B.f0 + issB : C.f0 + issC;
+                if (lane == 0) {
+                    const uint32_t bar = bars + 8 * is;
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(tmap), bx, by, plate, static_cast<int>(frame), bar);
+                }
+                is = is + 1 == D ? 0 : is + 1;
+                ++inflight;
+                if (fromA) ++issA;
+                else if (fromB) ++issB;
+                else ++issC;
+            };
+            while (inflight < D && (issA < A.nf || (b_box && issB < B.nf) || (c_box && issC < C.nf))) advance(0);
             // pixels of quad q (0..7): row (lane>>3) + 4q, columns 4*(lane&7) .. +3
             const uint32_t qx = tile_x + 4u * (lane & 7u), qy = tile_y + (lane >> 3);
-            uint32_t vmask[8], bgw[8];
-            uint32_t store_mask = 0xffu;
-            if (!full) {
-                store_mask = 0;
+            const size_t opx = RGBA ? 4 : 1;
+            uint8_t *out0 = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0) * p.out_stride + (static_cast<size_t>(qy) * width + qx) * opx;
+            const size_t row4 = static_cast<size_t>(width) * 4u * opx;   // four screen rows
+
+            // one frame: wait for its box, 32 byte loads from shared memory, pack, hand the stage on
+            auto gather_frame = [&](uint32_t (&b)[32], uint32_t (&w)[8]) {
+                mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
+                const uint32_t base = ring + cs * S;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) b[i] = lds_u8(base + off[i]);
+                if (RUBIX) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint4 &tv = tA[i >> 4];
+                        const uint32_t tw = ((i >> 2) & 3) == 0 ? tv.x : ((i >> 2) & 3) == 1 ? tv.y : ((i >> 2) & 3) == 2 ? tv.z : tv.w;
+                        // (tint byte << 8) + pixel value indexes the [7][256] LUT
+                        b[i] = lds_u8(lut_base + __byte_perm(tw, 0, 0x4404 | ((i & 3) << 4)) + b[i]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+                phases ^= 1u << cs;
+                cs = cs + 1 == D ? 0 : cs + 1;
+                --inflight;
+                advance(stage_dep(w, p.zero));
+            };
+
+            if (A.type == TILE_BOX_FULL) {
+                for (uint32_t f = 0; f < A.nf; ++f) {
+                    uint32_t b[32], w[8];
+                    gather_frame(b, w);
+                    uint8_t *o = out0 + static_cast<size_t>(f) * p.out_stride;
+                    if (RGBA) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            st_stream_v4(reinterpret_cast<uint4 *>(o + q * row4),
+                                         make_uint4(s_rgba[b[4 * q]], s_rgba[b[4 * q + 1]], s_rgba[b[4 * q + 2]], s_rgba[b[4 * q + 3]]));
+                    } else {
+                        uint64_t a[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = reinterpret_cast<uint64_t>(o + q * row4);
+                        st_stream_u32x8(a, w);
+                    }
+                }
+            } else {
+                // partly mapped tile, or one that hangs over the frame edge: per quad a byte mask of the
+                // mapped pixels, the background word for the others, and whether the quad is stored at all
+                uint32_t vmask[8], bgw[8];
+                uint32_t store_mask = 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint32_t w0 = q & 1 ? eA[q >> 1].z : eA[q >> 1].x, w1 = q & 1 ? eA[q >> 1].w : eA[q >> 1].y;
-                    // valid bits (bit 15 of each 16-bit entry) -> byte masks
-                    uint32_t m = 0;
+                    uint32_t m = 0;  // valid bits (bit 15 of each 16-bit entry) -> byte masks
                     if (w0 & 0x8000u) m |= 0x000000ffu;
                     if (w0 & 0x80000000u) m |= 0x0000ff00u;
                     if (w1 & 0x8000u) m |= 0x00ff0000u;
@@ -428,69 +511,17 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
                         if (m != 0xffffffffu) bgw[q] = __ldg(reinterpret_cast<const uint32_t *>(p.bg + static_cast<size_t>(y) * width + qx)) & ~m;
                     }
                 }
-            }
-            // one step of the look-ahead cursors: L2 prefetch runs PF boxes ahead of the TMA issue, the
-            // TMA issue up to D boxes ahead of the consumer; both walk A's frames, then B's first ones
-            auto advance = [&](uint32_t dep) {
-                if (inflight < D) {
-                    if (issA < A.nf) { issue_box(A.dy, A.dz, A.f0 + issA, dep); ++issA; }
-                    else if (b_box && issB < B.nf) { issue_box(B.dy, B.dz, B.f0 + issB, dep); ++issB; }
-                }
-                if (PF) {
-                    if (pfA < A.nf) { if (pfA < issA + PF) { prefetch_box(A.dy, A.dz, A.f0 + pfA); ++pfA; } }
-                    else if (b_box && pfB < B.nf && pfB < issB + PF + (A.nf - issA)) { prefetch_box(B.dy, B.dz, B.f0 + pfB); ++pfB; }
-                }
-            };
-            if (pfA < issA) pfA = issA;
-            while (inflight < D && issA < A.nf) advance(0);
-            for (uint32_t f = 0; f < A.nf; ++f) {
-                mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
-                const uint32_t base = ring + cs * S;
-                uint32_t b[32];
-                if (p.lab & 1u) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) b[i] = off[i] & 255u;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) b[i] = lds_u8(base + off[i]);
-                }
-                if (RUBIX) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint4 &tv = tA[i >> 4];
-                        const uint32_t tw = ((i >> 2) & 3) == 0 ? tv.x : ((i >> 2) & 3) == 1 ? tv.y : ((i >> 2) & 3) == 2 ? tv.z : tv.w;
-                        // (tint byte << 8) + pixel value indexes the [7][256] LUT
-                        b[i] = lds_u8(lut_base + __byte_perm(tw, 0, 0x4404 | ((i & 3) << 4)) + b[i]);
-                    }
-                }
-                uint32_t w[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) w[q] = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
-                const uint32_t dep = stage_dep(w, p.zero);
-                phases ^= 1u << cs;
-                cs = cs + 1 == D ? 0 : cs + 1;
-                --inflight;
-                // refill: this unit's next frame, else the first frames of the next BOX unit
-                advance(dep);
-                uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
-                if ((p.lab & 4u) && w[0] + w[7] != 12345u) continue;
-                if (full) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const size_t pix = static_cast<size_t>(qy + 4u * q) * width + qx;
-                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(out_frame) + (pix >> 2),
-                                               make_uint4(s_rgba[b[4 * q]], s_rgba[b[4 * q + 1]], s_rgba[b[4 * q + 2]], s_rgba[b[4 * q + 3]]));
-                        else st_stream_u32(reinterpret_cast<uint32_t *>(out_frame) + (pix >> 2), w[q]);
-                    }
-                } else {
+                for (uint32_t f = 0; f < A.nf; ++f) {
+                    uint32_t b[32], w[8];
+                    gather_frame(b, w);
+                    uint8_t *o = out0 + static_cast<size_t>(f) * p.out_stride;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (!((store_mask >> q) & 1u)) continue;
-                        const size_t pix = static_cast<size_t>(qy + 4u * q) * width + qx;
                         const uint32_t v = (w[q] & vmask[q]) | bgw[q];
-                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(out_frame) + (pix >> 2),
+                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(o + q * row4),
                                                make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
-                        else st_stream_u32(reinterpret_cast<uint32_t *>(out_frame) + (pix >> 2), v);
+                        else st_stream_u32(reinterpret_cast<uint32_t *>(o + q * row4), v);
                     }
                 }
             }
@@ -513,15 +544,22 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
                         e[r] = bgv;  // valid bit clear, low byte = background value
                     }
                 }
-                for (uint32_t f = 0; f < A.nf; ++f) {
-                    const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(A.f0 + f) * p.face_stride;
-                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
-                    uint32_t v[32];
+                // software pipeline over the frames: the 32 byte gathers of frame f+1 are in flight while
+                // frame f is written (these tiles are bound by global-load latency, not by bytes)
+                auto gather_frame = [&](uint32_t frame, uint32_t (&v)[32]) {
+                    const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(frame) * p.face_stride;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         v[r] = e[r] & 0xffu;
                         if (e[r] & BLINKY_LM_VALID) v[r] = ld_face(faces + (e[r] & BLINKY_LM_INDEX_MASK));
                     }
+                };
+                uint32_t v[32];
+                gather_frame(A.f0, v);
+                for (uint32_t f = 0; f < A.nf; ++f) {
+                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
+                    uint32_t vn[32];
+                    if (f + 1 < A.nf) gather_frame(A.f0 + f + 1, vn);
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         if (static_cast<uint32_t>(r) >= rows) break;
@@ -534,6 +572,8 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
                         if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[bv];
                         else out_frame[pix] = static_cast<uint8_t>(bv);
                     }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = vn[r];
                 }
             }
         } else {
@@ -556,7 +596,11 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
             }
         }
         // rotate: A <- B <- C <- the ticket drawn above
-        const uint32_t next_ticket = kStaticTickets * NW + (__shfl_sync(0xffffffffu, drawn, 0) - p.ticket_base);
+        uint32_t next_ticket = 0xffffffffu;
+        if (k_next < p.nstatic) next_ticket = blockIdx.x + k_next * NW;
+        else if (draw_dynamic) next_ticket = p.nstatic * NW + (__shfl_sync(0xffffffffu, drawn, 0) - p.ticket_base);
+        ++k_next;
+        last_good = next_ticket < p.nunits;
         A = B;
         B = C;
         C = describe(next_ticket);
@@ -565,9 +609,90 @@ __global__ void __launch_bounds__(32, 12) warp_ring_kernel(const __grid_constant
         tA[0] = tB[0];
         tA[1] = tB[1];
         issA = issB;
-        issB = 0;
-        pfA = pfB;
-        pfB = 0;
+        issB = issC;
+        issC = 0;
+    }
+}
+
+// --------------------------------------------------------------------------
+// K3: companion of the ring kernel for plans in which many tiles cannot be staged (GATHER: plate
+// seams, singular points, minification too strong for a 16 KB box; EMPTY: background only).  Those
+// tiles are bound by global-load latency, which one warp per tile hides badly; here they get plain
+// parallelism: grid = (tiles, groups of 4 frames), 256 threads, a warp owns 4 tile rows and lane l is
+// column l (one warp-level load = 32 consecutive screen pixels of one row).  The tile's entries are
+// fetched once and reused for the frames of the group; all 16 gathers of a thread are issued before
+// its first store.
+// --------------------------------------------------------------------------
+constexpr int kGatherFramesPerCta = 4;
+
+template <bool RUBIX, bool RGBA>
+__global__ void __launch_bounds__(kThreads) warp_tile_gather_kernel(const __grid_constant__ RingParams p, const uint32_t first_tile) {
+    const uint32_t tid = threadIdx.x;
+    const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + first_tile + blockIdx.x));
+    const uint32_t type = (d.z >> 8) & kTileTypeMask;
+    const uint32_t tile_x = d.w & 0xffffu, tile_y = d.w >> 16;
+    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
+    const uint32_t f0 = blockIdx.y * kGatherFramesPerCta;
+    const uint32_t f1 = min(f0 + kGatherFramesPerCta, p.nframes);
+
+    if (type == TILE_EMPTY) {
+        // quad layout: thread t copies 4 background pixels of row t/8
+        const uint32_t x = tile_x + (tid & 7u) * 4u, y = tile_y + (tid >> 3);
+        if (x >= width || y >= height) return;
+        const size_t pix = static_cast<size_t>(y) * width + x;
+        const uint32_t bgw = __ldg(reinterpret_cast<const uint32_t *>(p.bg + pix));
+        const uint32_t px[4] = {bgw & 0xffu, (bgw >> 8) & 0xffu, (bgw >> 16) & 0xffu, bgw >> 24};
+        for (uint32_t f = f0; f < f1; ++f) {
+            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
+            if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(o) + (pix >> 2), make_uint4(__ldg(p.rgba + px[0]), __ldg(p.rgba + px[1]), __ldg(p.rgba + px[2]), __ldg(p.rgba + px[3])));
+            else st_stream_u32(reinterpret_cast<uint32_t *>(o) + (pix >> 2), bgw);
+        }
+        return;
+    }
+
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t x = tile_x + lane;
+    const uint32_t *__restrict__ ent32 = reinterpret_cast<const uint32_t *>(p.entries + d.x);
+    uint32_t e[4], bgv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = __ldg(ent32 + (warp * 4 + j) * kTileW + lane);
+    if (x >= width) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t y = tile_y + warp * 4 + j;
+        bgv[j] = 0;
+        if (!(e[j] & BLINKY_LM_VALID) && y < height) bgv[j] = __ldg(p.bg + static_cast<size_t>(y) * width + x);
+    }
+    uint32_t v[kGatherFramesPerCta][4];
+#pragma unroll
+    for (int g = 0; g < kGatherFramesPerCta; ++g) {
+        const uint32_t f = f0 + g;
+        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f < f1 ? f : f0) * p.face_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[g][j] = bgv[j];
+            if (e[j] & BLINKY_LM_VALID) v[g][j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kGatherFramesPerCta; ++g) {
+        const uint32_t f = f0 + g;
+        if (f >= f1) break;
+        uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f) * p.out_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t y = tile_y + warp * 4 + j;
+            if (y < height) {
+                uint32_t b = v[g][j];
+                if (RUBIX && (e[j] & BLINKY_LM_VALID)) {
+                    const uint32_t t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
+                    if (t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
+                }
+                const size_t pix = static_cast<size_t>(y) * width + x;
+                if (RGBA) reinterpret_cast<uint32_t *>(o)[pix] = __ldg(p.rgba + b);
+                else o[pix] = static_cast<uint8_t>(b);
+            }
+        }
     }
 }
 
@@ -656,10 +781,13 @@ WarpDevice::WarpDevice(int device) : device_(device) {
     sm_count_ = prop.multiProcessorCount;
     if (const char *e = getenv("BLINKY_E2E_UPLOAD")) upload_by_kernel_ = strcmp(e, "kernel") == 0;
     if (const char *e = getenv("BLINKY_E2E_OUT")) out_by_kernel_ = strcmp(e, "direct") == 0;
+    if (const char *e = getenv("BLINKY_E2E_BATCH")) batch_copies_ = atoi(e) != 0;
     if (const char *e = getenv("BLINKY_RING_STAGES")) ring_stages_ = atoi(e);
     if (const char *e = getenv("BLINKY_RING_CTAS")) ring_ctas_cap_ = atoi(e);
     if (const char *e = getenv("BLINKY_FCHUNK")) fchunk_ = atoi(e);
-    if (const char *e = getenv("BLINKY_PREFETCH")) prefetch_ = atoi(e);
+    if (const char *e = getenv("BLINKY_SPLIT_PERCENT")) split_percent_ = atoi(e);
+    if (const char *e = getenv("BLINKY_RING_WARPS")) ring_minb_ = atoi(e);  // 12 (168 registers), 14 (144) or 16 (128) warps per SM
+    if (const char *e = getenv("BLINKY_STATIC_PCT")) static_pct_ = std::max(0, std::min(100, atoi(e)));
     if (const char *e = getenv("BLINKY_L2_PROMOTION")) l2_promotion_ = atoi(e) & 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B
     cudaStream_t s;
     e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -866,11 +994,28 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
     return t;
 }
 
-template <bool RUBIX, bool RGBA>
+// MINB = warps per SM the register allocation is sized for (168 registers at 12, 128 at 16)
+template <bool RUBIX, bool RGBA, int MINB>
 static cudaError_t ring_config(size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA>, 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA, MINB>, 32, smem);
+}
+
+template <int MINB>
+static cudaError_t ring_config_v(bool rubix, bool rgba, size_t smem, int *n) {
+    return rubix && rgba ? ring_config<true, true, MINB>(smem, n)
+           : rubix       ? ring_config<true, false, MINB>(smem, n)
+           : rgba        ? ring_config<false, true, MINB>(smem, n)
+                         : ring_config<false, false, MINB>(smem, n);
+}
+
+template <int MINB>
+static void ring_launch_v(bool rubix, bool rgba, uint32_t grid, size_t smem, cudaStream_t st, const RingParams &p, const RingTmaps &tm) {
+    if (rubix && rgba) warp_ring_kernel<true, true, MINB><<<grid, 32, smem, st>>>(p, tm);
+    else if (rubix) warp_ring_kernel<true, false, MINB><<<grid, 32, smem, st>>>(p, tm);
+    else if (rgba) warp_ring_kernel<false, true, MINB><<<grid, 32, smem, st>>>(p, tm);
+    else warp_ring_kernel<false, false, MINB><<<grid, 32, smem, st>>>(p, tm);
 }
 
 bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
@@ -900,23 +1045,23 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     p.width = width_;
     p.height = height_;
     p.zero = 0;
-    p.lab = 0;
-    if (const char *e = getenv("BLINKY_LAB")) p.lab = static_cast<uint32_t>(atoi(e));
-    p.prefetch = static_cast<uint32_t>(prefetch_);
-    p.platesize = platesize_;
     const bool rubix = rubix_;
     const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
+    // Tiles [0, nbox) are BOX tiles.  A few GATHER/EMPTY tiles ride along in the ring kernel (one launch,
+    // one warp each, frames software-pipelined); when they are many (strong minification, large unmapped
+    // borders) they go to the gather kernel K3, which hides their load latency with plain parallelism.
+    const bool split = (ntiles_ - nbox_tiles_) * 100u > ntiles_ * static_cast<uint32_t>(split_percent_);
+    const uint32_t ring_tiles = split ? nbox_tiles_ : ntiles_;
     // ring geometry: stages hold the plan's largest box
     p.stage_bytes = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
-    p.nstages = ring_stages_ > 0 ? static_cast<uint32_t>(ring_stages_) : (p.stage_bytes <= 4096 ? 3u : 2u);
+    // two stages per warp keep a multi-frame unit fed; single-frame launches (the in-engine shape) consume a
+    // stage per unit and want one more box in flight
+    p.nstages = ring_stages_ > 0 ? static_cast<uint32_t>(ring_stages_) : (p.stage_bytes <= 4096 || (nframes == 1 && p.stage_bytes <= 8192) ? 3u : 2u);
     if (p.nstages > static_cast<uint32_t>(kRingMaxStages)) p.nstages = kRingMaxStages;
     const size_t smem = static_cast<size_t>(p.stage_bytes) * p.nstages + kRingMaxStages * 8 + (rubix ? 7 * 256 : 0) + (rgba ? 1024 : 0);
     if (ring_ctas_per_sm_[vi] == 0 || ring_smem_[vi] != smem) {
         int n = 0;
-        cudaError_t e = rubix && rgba ? ring_config<true, true>(smem, &n)
-                        : rubix       ? ring_config<true, false>(smem, &n)
-                        : rgba        ? ring_config<false, true>(smem, &n)
-                                      : ring_config<false, false>(smem, &n);
+        cudaError_t e = ring_minb_ == 16 ? ring_config_v<16>(rubix, rgba, smem, &n) : ring_minb_ == 14 ? ring_config_v<14>(rubix, rgba, smem, &n) : ring_config_v<12>(rubix, rgba, smem, &n);
         if (e != cudaSuccess) return fail("ring kernel configuration (shared memory / occupancy)", e);
         if (n < 1) {
             err_ = "ring kernel does not fit on an SM";
@@ -928,54 +1073,80 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     int ctas = ring_ctas_per_sm_[vi];
     if (ring_ctas_cap_ > 0 && ctas > ring_ctas_cap_) ctas = ring_ctas_cap_;
     uint32_t grid = static_cast<uint32_t>(sm_count_ * ctas);
-    // frames per unit: enough units per warp for the dynamic schedule to balance, few enough that a
-    // unit's entry unpack is spread over several frames
-    uint32_t fchunk = fchunk_ > 0 ? static_cast<uint32_t>(fchunk_) : static_cast<uint32_t>(static_cast<uint64_t>(nframes) * ntiles_ / (12ull * grid));
-    if (fchunk < 1) fchunk = 1;
-    if (fchunk_ <= 0 && fchunk > 8) fchunk = 8;
+    // frames per unit: a unit pays a fixed cost (entry unpack, ring refill across the boundary: ~0.8 frame
+    // times) and the launch ends with a tail of about one unit; pick the chunk that minimises
+    // units-per-warp x (chunk + 0.8) + chunk
+    uint32_t fchunk = fchunk_ > 0 ? static_cast<uint32_t>(fchunk_) : 1;
+    if (fchunk_ <= 0) {
+        double best = 0;
+        for (uint32_t c = 1; c <= std::min<uint32_t>(p.nframes, 16u); ++c) {
+            const double units = static_cast<double>(ring_tiles) * ((p.nframes + c - 1) / c);
+            const double cost = std::max(1.0, units / grid) * (c + 0.8) + c;
+            if (c == 1 || cost < best) best = cost, fchunk = c;
+        }
+    }
     if (fchunk > p.nframes) fchunk = p.nframes;
     p.fchunk = fchunk;
     p.nchunks = (p.nframes + fchunk - 1) / fchunk;
-    p.nunits = ntiles_ * p.nchunks;
+    p.nunits = ring_tiles * p.nchunks;
     if (grid > p.nunits) grid = p.nunits;
-    if (grid == 0) return true;
-    // ticket counter of this stream (launches on one stream are serialised; the counter is never reset:
-    // the kernel subtracts the value it had when the launch started)
-    TicketCounter *tc = nullptr;
-    for (TicketCounter &c : tickets_)
-        if (c.stream == stream) tc = &c;
-    if (!tc) {
-        if (tickets_.size() >= 64) {  // streams come and go: start over
-            CK(cudaDeviceSynchronize());
-            for (TicketCounter &c : tickets_) cudaFree(c.d_counter);
-            tickets_.clear();
+    char buf[512];
+    int nbuf = 0;
+    if (grid > 0) {
+        // ticket counter of this stream (launches on one stream are serialised; the counter is never reset:
+        // the kernel subtracts the value it had when the launch started)
+        TicketCounter *tc = nullptr;
+        for (TicketCounter &c : tickets_)
+            if (c.stream == stream) tc = &c;
+        if (!tc) {
+            if (tickets_.size() >= 64) {  // streams come and go: start over
+                CK(cudaDeviceSynchronize());
+                for (TicketCounter &c : tickets_) cudaFree(c.d_counter);
+                tickets_.clear();
+            }
+            TicketCounter c;
+            c.stream = stream;
+            c.base = 0;
+            CK(cudaMalloc(&c.d_counter, sizeof(uint32_t)));
+            CK(cudaMemsetAsync(c.d_counter, 0, sizeof(uint32_t), st));
+            tickets_.push_back(c);
+            tc = &tickets_.back();
         }
-        TicketCounter c;
-        c.stream = stream;
-        c.base = 0;
-        CK(cudaMalloc(&c.d_counter, sizeof(uint32_t)));
-        CK(cudaMemsetAsync(c.d_counter, 0, sizeof(uint32_t), st));
-        tickets_.push_back(c);
-        tc = &tickets_.back();
-    }
-    p.ticket = tc->d_counter;
-    p.ticket_base = tc->base;
-    // draws of this launch: every unit beyond the static ones is drawn once, and every warp whose last
-    // static ticket was good draws exactly one ticket past the end
-    const uint64_t nstatic = static_cast<uint64_t>(kStaticTickets) * grid;
-    const uint32_t good = p.nunits > nstatic ? static_cast<uint32_t>(p.nunits - nstatic) : 0u;
-    const uint64_t two = static_cast<uint64_t>(kStaticTickets - 1) * grid;
-    const uint32_t drawers = p.nunits > two ? static_cast<uint32_t>(std::min<uint64_t>(p.nunits - two, grid)) : 0u;
-    tc->base += good + drawers;
+        p.ticket = tc->d_counter;
+        p.ticket_base = tc->base;
+        // static share of the schedule (see the kernel): static_pct_ percent of the units, whole rounds
+        uint32_t nstatic = static_cast<uint32_t>(static_cast<uint64_t>(p.nunits) * static_cast<uint64_t>(static_pct_) / 100u / grid);
+        p.nstatic = nstatic;
+        // draws of this launch: every unit beyond the static ones is drawn exactly once, and every warp that
+        // draws at all draws exactly one ticket past the end (it stops at its first bad ticket).  A warp draws
+        // iff its last static ticket is good (all warps when there are no static rounds).
+        const uint64_t nst = static_cast<uint64_t>(nstatic) * grid;
+        const uint32_t good = p.nunits > nst ? static_cast<uint32_t>(p.nunits - nst) : 0u;
+        uint32_t drawers = grid;
+        if (nstatic > 0) {
+            const uint64_t before_last = static_cast<uint64_t>(nstatic - 1) * grid;
+            drawers = p.nunits > before_last ? static_cast<uint32_t>(std::min<uint64_t>(p.nunits - before_last, grid)) : 0u;
+        }
+        tc->base += good + drawers;
 
-    if (rubix && rgba) warp_ring_kernel<true, true><<<grid, 32, smem, st>>>(p, *tm);
-    else if (rubix) warp_ring_kernel<true, false><<<grid, 32, smem, st>>>(p, *tm);
-    else if (rgba) warp_ring_kernel<false, true><<<grid, 32, smem, st>>>(p, *tm);
-    else warp_ring_kernel<false, false><<<grid, 32, smem, st>>>(p, *tm);
-    ++launches_;
-    char buf[320];
-    snprintf(buf, sizeof buf, "warp_ring_kernel<rubix=%d,rgba=%d> grid=%u block=32 (%d warps/SM, %u-stage TMA ring of %u B, %u frames/unit, %u units)", rubix,
-             rgba, grid, ctas, p.nstages, p.stage_bytes, fchunk, p.nunits);
+        if (ring_minb_ == 16) ring_launch_v<16>(rubix, rgba, grid, smem, st, p, *tm);
+        else if (ring_minb_ == 14) ring_launch_v<14>(rubix, rgba, grid, smem, st, p, *tm);
+        else ring_launch_v<12>(rubix, rgba, grid, smem, st, p, *tm);
+        ++launches_;
+        nbuf = snprintf(buf, sizeof buf, "warp_ring_kernel<rubix=%d,rgba=%d> grid=%u block=32 (%d warps/SM, %u-stage TMA ring of %u B, %u frames/unit, %u units)", rubix,
+                        rgba, grid, ctas, p.nstages, p.stage_bytes, fchunk, p.nunits);
+    }
+    const uint32_t nother = ntiles_ - ring_tiles;
+    if (nother > 0) {
+        dim3 g2(nother, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
+        if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else if (rubix) warp_tile_gather_kernel<true, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else if (rgba) warp_tile_gather_kernel<false, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        else warp_tile_gather_kernel<false, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
+        ++launches_;
+        snprintf(buf + nbuf, sizeof buf - static_cast<size_t>(nbuf), "%swarp_tile_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", nbuf ? " + " : "", rubix,
+                 rgba, g2.x, g2.y, kThreads);
+    }
     last_kernel_ = buf;
     CK(cudaGetLastError());
     return true;
@@ -1092,8 +1263,10 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
     CK(cudaSetDevice(device_));
     if (!ensure_slots()) return false;
     const size_t ps2 = static_cast<size_t>(platesize_) * platesize_;
-    const bool src_pinned = is_pinned(faces_host);
-    const bool dst_pinned = is_pinned(dst_host);
+    // (one driver query per distinct buffer, not two per call)
+    if (faces_host != pin_src_ptr_) pin_src_ptr_ = faces_host, pin_src_ = is_pinned(faces_host);
+    if (dst_host != pin_dst_ptr_) pin_dst_ptr_ = dst_host, pin_dst_ = is_pinned(dst_host);
+    const bool src_pinned = pin_src_, dst_pinned = pin_dst_;
     const int W = width_, H = height_;
     bool ok = true;
     for (int f = 0; f < nframes && ok; ++f) {
@@ -1108,6 +1281,8 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
         ur.first[0] = 0;
         ur.pitch = static_cast<uint32_t>(platesize_);
         const bool by_kernel = upload_by_kernel_ && platesize_ % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 && face_stride % 16 == 0;
+        cudaMemcpy3DBatchOp ops[BLINKY_MAX_PLATES];
+        size_t nops = 0;
         for (int pl = 0; pl < numplates_; ++pl) {
             if (!display_[pl]) continue;
             const int *r = plate_rect_[pl];
@@ -1128,9 +1303,38 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
                 for (size_t y = 0; y < rh; ++y) memcpy(s.h_faces + off + y * platesize_, from + y * platesize_, rw);
                 from = s.h_faces + off;
             }
+            if (batch_copies_) {  // all rectangles of the frame in ONE driver call (no gap between six DMA operations)
+                cudaMemcpy3DBatchOp &op = ops[nops++];
+                memset(&op, 0, sizeof op);
+                op.src.type = cudaMemcpyOperandTypePointer;
+                op.src.op.ptr.ptr = const_cast<uint8_t *>(from);
+                op.src.op.ptr.rowLength = static_cast<size_t>(platesize_);
+                op.src.op.ptr.layerHeight = rh;
+                op.dst.type = cudaMemcpyOperandTypePointer;
+                op.dst.op.ptr.ptr = s.d_faces + off;
+                op.dst.op.ptr.rowLength = static_cast<size_t>(platesize_);
+                op.dst.op.ptr.layerHeight = rh;
+                op.extent = make_cudaExtent(rw, rh, 1);
+                op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                continue;
+            }
             cudaError_t e = cudaMemcpy2DAsync(s.d_faces + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
                                               cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
+        }
+        if (ok && nops > 0) {
+            size_t fail_idx = 0;
+            cudaError_t e = cudaMemcpy3DBatchAsync(nops, ops, &fail_idx, 0, s.stream);
+            if (e != cudaSuccess) {
+                // not available on this driver: fall back to one 2-D copy per plate, from now on
+                cudaGetLastError();
+                batch_copies_ = false;
+                for (size_t k = 0; k < nops && ok; ++k) {
+                    e = cudaMemcpy2DAsync(ops[k].dst.op.ptr.ptr, static_cast<size_t>(platesize_), ops[k].src.op.ptr.ptr, static_cast<size_t>(platesize_),
+                                          ops[k].extent.width, ops[k].extent.height, cudaMemcpyHostToDevice, s.stream);
+                    if (e != cudaSuccess) ok = fail("cudaMemcpy2DAsync(H2D faces)", e);
+                }
+            }
         }
         if (ok && ur.n > 0) {
             const uint32_t total = ur.first[ur.n];

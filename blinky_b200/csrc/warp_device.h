@@ -73,6 +73,9 @@ private:
     int sm_count_ = 148;
     void *stream_ = nullptr;  // cudaStream_t
     bool upload_by_kernel_ = false, out_by_kernel_ = false;  // warp_host variants (BLINKY_E2E_UPLOAD / BLINKY_E2E_OUT)
+    bool batch_copies_ = true;   // plate rectangles of a frame in one cudaMemcpy3DBatchAsync (BLINKY_E2E_BATCH=0: one 2-D copy each)
+    const void *pin_src_ptr_ = nullptr, *pin_dst_ptr_ = nullptr;  // last buffers warp_host saw and whether they are pinned
+    bool pin_src_ = false, pin_dst_ = false;
     std::string err_;
 
     // resident lensmap
@@ -103,8 +106,10 @@ private:
     uint8_t *d_entries_ = nullptr;
     uint32_t ntiles_ = 0, nbox_tiles_ = 0, ngather_tiles_ = 0;
     int stage_bytes_ = 0;                // largest staged box of the plan
-    int prefetch_ = 0;                   // L2 prefetch distance of the ring kernel, boxes (BLINKY_PREFETCH)
+    int ring_minb_ = 12;                 // warps per SM the ring kernel's registers are sized for (BLINKY_RING_WARPS: 12, 14, 16)
+    int static_pct_ = 85;                // share of the ring kernel's units scheduled statically (BLINKY_STATIC_PCT)
     int l2_promotion_ = 0;               // CUtensorMapL2promotion of the box descriptors (BLINKY_L2_PROMOTION)
+    int split_percent_ = 12;             // GATHER+EMPTY share of tiles above which they get their own kernel (BLINKY_SPLIT_PERCENT)
     int ring_stages_ = 0, ring_ctas_cap_ = 0, fchunk_ = 0;  // tuning overrides (BLINKY_RING_STAGES / _CTAS, BLINKY_FCHUNK); 0 = automatic
     std::vector<uint16_t> shapes_;
     std::vector<TmapSet *> tmap_sets_;   // small cache keyed by (faces ptr, stride, nframes)

@@ -3,8 +3,10 @@
 The warp of one frame is independent of every other frame (the lensmap is replicated —
 each rank rebuilds it deterministically from the same scripts), so a batch shards with NO
 collective on the data path.  The only exchange is the reference topology's final step:
-finished frames travel to rank 0 (the one display), done here with torch.distributed
-point-to-point ops (NCCL over NVLink on GPUs, gloo in the CPU tests).
+finished frames travel to rank 0 (the one display).  The product path for that is the C ABI's
+blinky_shard_warp_gather (include/blinky_b200.h: NCCL send/recv or NVLink peer memory, overlapped with
+the warp); gather_frames below is the same exchange with torch.distributed point-to-point ops — used
+by the CPU tests (gloo) and as the cross-check of the C path in bench.py.
 """
 from __future__ import annotations
 
@@ -15,10 +17,11 @@ import torch.distributed as dist
 
 
 def frames_for_rank(total_frames: int, rank: int, world: int) -> range:
-    """contiguous block of global frame ids owned by `rank` (sizes differ by at most one)"""
-    base, extra = divmod(total_frames, world)
-    start = rank * base + min(rank, extra)
-    return range(start, start + base + (1 if rank < extra else 0))
+    """contiguous block of global frame ids owned by `rank` (sizes differ by at most one) — the C ABI's
+    blinky_shard_range, the one partition rule every gather path (NCCL, peer copy, peer store, gloo) uses"""
+    from . import shard_range
+
+    return shard_range(total_frames, rank, world)
 
 
 def gather_frames(local: torch.Tensor, rank: int, world: int, total_frames: Optional[int] = None,

@@ -390,6 +390,204 @@ static int quincuncial_inverse(double x, double y, double o[3], void *ud)
     return q_inverse_intermediate(x0, y0, o);
 }
 
+
+/* ---- lenses/mollweide.lua --------------------------------------------------- */
+static double mollweide_solveTheta(double lat)
+{ /* :11-19 — Newton iteration, `repeat ... until dt < 0.001` (signed test, as written) */
+    double t = lat, dt;
+    do {
+        dt = -(t + sin(t) - pi * sin(lat)) / (1 + cos(t));
+        t = t + dt;
+    } while (!(dt < 0.001));
+    return t / 2;
+}
+
+static int mollweide_inverse(double x, double y, double o[3], void *ud)
+{ /* :21-29 */
+    (void)ud;
+    const double root2 = sqrt(2); /* :1 */
+    if (x * x / 8 + y * y / 2 > 1) return 0;
+    double t = asin(y / root2);
+    double lon = pi * x / (2 * root2 * cos(t));
+    double lat = asin((2 * t + sin(2 * t)) / pi);
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int mollweide_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :31-37 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double t = mollweide_solveTheta(lat);
+    *ox = 2 * sqrt(2) / pi * lon * cos(t);
+    *oy = sqrt(2) * sin(t);
+    return 1;
+}
+
+/* ---- lenses/vandergrinten.lua ---------------------------------------------- */
+static int vandergrinten_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :6-35 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    if (lat == 0) {
+        *ox = lon;
+        *oy = 0;
+        return 1;
+    }
+    double t = asin(fabs(2 * lat / pi));
+    if (fabs(lat) == pi / 2) {
+        double y2 = pi * tan(t / 2);
+        if (y2 * lat < 0) y2 = -y2;
+        *ox = 0;
+        *oy = y2;
+        return 1;
+    }
+    double a = 0.5 * fabs(pi / lon - lon / pi);
+    double g = cos(t) / (sin(t) + cos(t) - 1);
+    double p = g * (2 / sin(t) - 1);
+    double q = a * a + g;
+    double xx = pi * (a * (g - p * p) + sqrt(a * a * (g - p * p) * (g - p * p) - (p * p + a * a) * (g * g - p * p))) / (p * p + a * a);
+    double yy = pi * (p * q - a * sqrt((a * a + 1) * (p * p + a * a) - q * q)) / (p * p + a * a);
+    if (lon * xx < 0) xx = -xx;
+    if (lat * yy < 0) yy = -yy;
+    *ox = xx;
+    *oy = yy;
+    return 1;
+}
+
+static double vandergrinten_maxr(void)
+{ /* :109 — maxr = lens_forward(latlon_to_ray(0,pi)): the first of the two results */
+    double r[3], mx, my;
+    orc_lua_latlon_to_ray(0, pi, r);
+    vandergrinten_forward(r[0], r[1], r[2], &mx, &my, NULL);
+    return mx;
+}
+
+static int vandergrinten_inverse(double x, double y, double o[3], void *ud)
+{ /* :46-107 (constants :37-44) */
+    (void)ud;
+    const double TOL = 1.e-10, THIRD = .33333333333333333333, C2_27 = .07407407407407407407, PI4_3 = 4.18879020478639098458,
+                 PISQ = 9.86960440108935861869, TPISQ = 19.73920880217871723738, HPISQ = 4.93480220054467930934;
+    const double maxr = vandergrinten_maxr();
+    if (x * x + y * y > maxr * maxr) return 0;
+    double lat, lon;
+    double t, c0, c1, c2, c3, al, r2, r, m, d, ay, x2, y2;
+    x2 = x * x;
+    ay = fabs(y);
+    if (ay < TOL) {
+        lat = 0;
+        t = x2 * x2 + TPISQ * (x2 + HPISQ);
+        if (fabs(x) <= TOL) lon = 0;
+        else lon = 0.5 * (x2 - PISQ + sqrt(t)) / x;
+        orc_lua_latlon_to_ray(lat, lon, o);
+        return 1;
+    }
+    y2 = y * y;
+    r = x2 + y2;
+    r2 = r * r;
+    c1 = -pi * ay * (r + PISQ);
+    c3 = r2 + (2 * pi) * (ay * r + pi * (y2 + pi * (ay + pi / 2)));
+    c2 = c1 + PISQ * (r - 3 * y2);
+    c0 = pi * ay;
+    c2 = c2 / c3;
+    al = c1 / c3 - THIRD * c2 * c2;
+    m = 2 * sqrt(-THIRD * al);
+    d = C2_27 * c2 * c2 * c2 + (c0 * c0 - THIRD * c2 * c1) / c3;
+    d = 3 * d / (al * m);
+    t = fabs(d);
+    if (t - TOL <= 1) {
+        if (t > 1) {
+            if (d > 0) d = 0;
+            else d = pi;
+        } else {
+            d = acos(d);
+        }
+        lat = pi * (m * cos(d * THIRD + PI4_3) - THIRD * c2);
+        if (y < 0) lat = -lat;
+        t = r2 + TPISQ * (x2 - y2 + HPISQ);
+        if (fabs(x) <= TOL) {
+            lon = 0;
+        } else {
+            if (t <= 0) lon = 0.5 * (r - PISQ) / x;
+            else lon = 0.5 * (r - PISQ + sqrt(t)) / x;
+        }
+    } else {
+        return 0;
+    }
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+/* ---- lenses/cube.lua -------------------------------------------------------- */
+static void cube_modf_cell(double n, double *i, double *f)
+{ /* col()/row() :12-28: math.modf, cells left of / above zero shifted down by one */
+    double ip;
+    double fp = modf(n, &ip);
+    if (n < 0) {
+        *i = ip - 1;
+        *f = fp + 1;
+    } else {
+        *i = ip;
+        *f = fp;
+    }
+}
+
+static int cube_inverse(double x, double y, double o[3], void *ud)
+{ /* :30-71 */
+    (void)ud;
+    const double cols = 4, rows = 3;
+    double r, v, c, u;
+    x = x - 0.5;
+    cube_modf_cell(-y + rows / 2, &r, &v);
+    cube_modf_cell(x + cols / 2, &c, &u);
+    u = u - 0.5;
+    v = v - 0.5;
+    v = -v;
+    if (r < 0 || r >= rows || c < -1 || c >= cols) return 0;
+    if (r == 0 || r == 2) {
+        if (!(c == 1)) return 0;
+    }
+    if (r == 0) { o[0] = u; o[1] = 0.5; o[2] = -v; }          /* top */
+    else if (r == 2) { o[0] = u; o[1] = -0.5; o[2] = v; }     /* bottom */
+    else if (c == 0) { o[0] = -0.5; o[1] = v; o[2] = u; }     /* left */
+    else if (c == 1) { o[0] = u; o[1] = v; o[2] = 0.5; }      /* front */
+    else if (c == 2) { o[0] = 0.5; o[1] = v; o[2] = -u; }     /* right */
+    else if (c == 3 || c == -1) { o[0] = -u; o[1] = v; o[2] = -0.5; } /* back */
+    else return 0;
+    return 1;
+}
+
+static int cube_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :73-125 — "only to be used for FOV" */
+    (void)ud;
+    double ax = fabs(x), ay = fabs(y), az = fabs(z);
+    double mx = ax > ay ? ax : ay; /* math.max(ax,ay,az) */
+    mx = mx > az ? mx : az;
+    double u, v;
+    if (mx == ax) {
+        if (x > 0) { u = -z / x * 0.5; v = y / x * 0.5; *ox = 1 + u; *oy = v; }
+        else { u = z / -x * 0.5; v = y / -x * 0.5; *ox = -1 + u; *oy = v; }
+        return 1;
+    } else if (mx == ay) {
+        if (y > 0) { u = x / y * 0.5; v = -z / y * 0.5; *ox = u; *oy = 1 + v; }
+        else { u = x / -y * 0.5; v = z / -y * 0.5; *ox = u; *oy = -1 + v; }
+        return 1;
+    } else if (mx == az) {
+        if (z > 0) { u = x / z * 0.5; v = y / z * 0.5; *ox = u; *oy = v; }
+        else {
+            u = -x / -z * 0.5;
+            v = y / -z * 0.5;
+            if (u > 0) *ox = -2 + u;
+            else *ox = 2 + u;
+            *oy = v;
+        }
+        return 1;
+    }
+    return -1; /* the script falls off its end: no values */
+}
+
 /* ---- registry --------------------------------------------------------------- */
 int orc_find_lens(const char *name, orc_lens_def *out)
 {
@@ -420,6 +618,17 @@ int orc_find_lens(const char *name, orc_lens_def *out)
     } else if (!strcmp(name, "fisheye1")) {
         out->inverse = fisheye1_inverse; out->forward = fisheye1_forward;
         out->max_fov = 360; out->max_vfov = 360; out->lens_width = 2 * pi; out->lens_height = 2 * pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "mollweide")) {
+        out->inverse = mollweide_inverse; out->forward = mollweide_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = 2 * sqrt(2) * 2; out->lens_height = sqrt(2) * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "vandergrinten")) {
+        out->inverse = vandergrinten_inverse; out->forward = vandergrinten_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = 2 * vandergrinten_maxr(); out->lens_height = 2 * vandergrinten_maxr(); out->onload = "f_contain";
+    } else if (!strcmp(name, "cube")) {
+        out->inverse = cube_inverse; out->forward = cube_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 4; out->lens_height = 3; out->onload = "f_contain";
     } else if (!strcmp(name, "fisheye2")) {
         double maxr = 2 * sin(pi * 0.5);
         out->inverse = fisheye2_inverse; out->forward = fisheye2_forward;

@@ -34,15 +34,18 @@
 #include "engine_stubs.inc"
 
 blinky_ctx *F_B200_Context(void);
+int F_B200_Building(void);
+void F_B200_WaitBuild(void);
+int F_B200_ShownDisplay(int *display, int *numplates);
 
 static int harness_displayed_plate(int k, int *platesize)
 {
-    int display[BLINKY_MAX_PLATES], seen = 0;
+    int display[BLINKY_MAX_PLATES], seen = 0, numplates = 0;
     blinky_ctx *c = F_B200_Context();
     if (!c) return -1;
     *platesize = scr_vrect.width < scr_vrect.height ? scr_vrect.width : scr_vrect.height;
-    blinky_get_display(c, display);
-    for (int i = 0; i < blinky_numplates(c); i++) {
+    F_B200_ShownDisplay(display, &numplates); /* the plates of the lensmap that is on screen */
+    for (int i = 0; i < numplates; i++) {
         if (display[i]) {
             if (seen == k) return i;
             seen++;
@@ -99,12 +102,33 @@ int dropin_set_screen(int w, int h, int rowbytes, int vx, int vy, int vw, int vh
     return 0;
 }
 
+/* one F_RenderView call; the lensmap rebuild it may start runs on the drop-in's worker thread */
+int dropin_frame_nowait(const unsigned char *faces, const unsigned char *background, unsigned char *out)
+{
+    g_faces = faces;
+    g_background = background;
+    g_render_calls = 0;
+    F_RenderView();
+    if (out) memcpy(out, vid.buffer, (size_t)vid.rowbytes * vid.height);
+    g_faces = NULL;
+    g_background = NULL;
+    return g_render_calls;
+}
+int dropin_building(void) { return F_B200_Building(); }
+
+/* the frame a viewer sees once a pending rebuild has finished: F_RenderView (which starts the rebuild
+ * if the console changed anything), wait for the worker, F_RenderView again */
 int dropin_frame(const unsigned char *faces, const unsigned char *background, unsigned char *out)
 {
     g_faces = faces;
     g_background = background;
     g_render_calls = 0;
     F_RenderView();
+    if (F_B200_Building()) {
+        F_B200_WaitBuild();
+        g_render_calls = 0;
+        F_RenderView();
+    }
     if (out) memcpy(out, vid.buffer, (size_t)vid.rowbytes * vid.height);
     g_faces = NULL;
     g_background = NULL;

@@ -91,3 +91,56 @@ def test_dropin_matches_compiled_reference(bb, ref, palette, cuda_device):
     D.dropin_write_config(b"/tmp/_dropin_cfg.txt")
     assert open("/tmp/_dropin_cfg.txt").read() == ref.write_config("/tmp/_ref_cfg2.txt")
     D.dropin_shutdown()
+
+
+@needs_so
+@pytest.mark.gpu
+def test_dropin_rebuild_never_holds_a_frame_up(bb, ref, palette, cuda_device):
+    """The reference's lens builder is time-sliced so that no frame waits for it (engine/NQ/fisheye.c:744-746,
+    819-826).  The drop-in builds on a worker thread in a second context: across an f_lens change every
+    F_RenderView call must return within a frame time, frames shown meanwhile are the PREVIOUS lens's,
+    and the frame after the swap is the reference's frame for the new lens."""
+    import time
+
+    D = ctypes.CDLL(SO)
+    D.dropin_log.restype = ctypes.c_char_p
+    assert D.dropin_init(bb.SCRIPT_DIR.encode(), palette.ctypes.data_as(ctypes.c_void_p)) == 0
+    w, h = 640, 480
+    ps = min(w, h)
+
+    def both(cmd):
+        ref.command(cmd)
+        D.dropin_command(cmd.encode())
+
+    for c in ("fisheye 1", "f_globe cube", "f_lens panini", "f_fov 180"):
+        both(c)
+    if ref.rubix_enabled:
+        ref.command("f_rubix")
+    ref.set_screen(w, h, w, 0, 0, w, h)
+    D.dropin_set_screen(w, h, w, 0, 0, w, h)
+    faces = bb.synthetic_faces(6, ps, 9)
+    bg = np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)
+    fp, bp = faces.ctypes.data_as(ctypes.c_void_p), bg.ctypes.data_as(ctypes.c_void_p)
+    old = np.zeros((h, w), np.uint8)
+    D.dropin_frame(fp, bp, old.ctypes.data_as(ctypes.c_void_p))          # panini, built and shown
+    want_old, _ = ref.frame(faces, bg)
+    assert np.array_equal(old, want_old)
+
+    both("f_lens winkeltripel")   # an expensive lens: NVRTC + thousands of interpreter re-evaluations
+    both("f_contain")
+    times, during = [], []
+    got = np.zeros((h, w), np.uint8)
+    for it in range(100000):
+        t0 = time.perf_counter()
+        D.dropin_frame_nowait(fp, bp, got.ctypes.data_as(ctypes.c_void_p))
+        times.append(time.perf_counter() - t0)
+        if not D.dropin_building():
+            break
+        during.append(got.copy())
+    assert len(times) >= 2, "the rebuild finished inside the first F_RenderView call: it was not asynchronous"
+    assert max(times) < 1 / 60 + 0.010, f"a frame waited {max(times) * 1e3:.1f} ms for the lens build"
+    assert all(np.array_equal(f, want_old) for f in during[:50]), "frames during the build must show the previous lensmap"
+    D.dropin_frame_nowait(fp, bp, got.ctypes.data_as(ctypes.c_void_p))     # first frame after the swap
+    want_new, _ = ref.frame(faces, bg)
+    assert np.array_equal(got, want_new)
+    D.dropin_shutdown()

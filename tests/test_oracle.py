@@ -15,6 +15,7 @@ from conftest import sha
 from oracle.pyoracle import TRANSCRIBED_GLOBES, TRANSCRIBED_LENSES
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMALL = (128, 96, 48)
 
 
@@ -192,3 +193,24 @@ def test_transcribed_lenses_equal_the_scripts_per_call(restate, host):
             assert st_c == st_p
             if st_c == 1:
                 assert np.array_equal(np.array(xy_c).view(np.uint64), np.array(xy_p).view(np.uint64)), (l, v)
+
+
+def test_fastmath_drift(ref):
+    """The reference ships with -ffast-math (engine/Makefile:270-277); the oracle is the same source without it.
+    scripts/fastmath_drift.py builds every lens with both compiled references and counts differing lensmap entries
+    (committed numbers: profiles/r2_fastmath_drift.txt).  Here: the machinery works and the drift stays what the
+    report says — a handful of pixels landing on the neighbouring texel, never a mapped<->unmapped flip."""
+    import io
+    import sys
+
+    from oracle.pyoracle import RefOracle
+
+    if not RefOracle.available(fastmath=True):
+        pytest.skip("oracle/_ref/libblinky_ref_fastmath.so not built")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fastmath_drift
+
+    rows = fastmath_drift.drift(lenses=["panini", "stereographic", "equirect", "quincuncial"], size=(320, 200, 128), out=io.StringIO(), exact=ref)
+    for lens, ndiff, flips, dx, dy in rows:
+        assert ndiff <= 0.01 * 320 * 200 and flips == 0 and dx <= 1 and dy <= 1, (lens, ndiff, flips, dx, dy)
+    assert os.path.exists(os.path.join(ROOT, "profiles", "r2_fastmath_drift.txt"))

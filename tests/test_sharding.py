@@ -57,6 +57,22 @@ def test_gather_to_rank0_gloo(world, total):
     assert all(results)
 
 
+def test_shard_range_c_entry_rejects_bad_arguments(bb):
+    import ctypes
+
+    lib = bb.load_library()
+    f, c = ctypes.c_int(), ctypes.c_int()
+    assert lib.blinky_shard_range(8, 0, 2, ctypes.byref(f), ctypes.byref(c)) == 0 and (f.value, c.value) == (0, 4)
+    assert lib.blinky_shard_range(8, 2, 2, ctypes.byref(f), ctypes.byref(c)) == bb.E_INVALID
+    assert lib.blinky_shard_range(8, 0, 0, ctypes.byref(f), ctypes.byref(c)) == bb.E_INVALID
+    assert lib.blinky_shard_range(-1, 0, 1, ctypes.byref(f), ctypes.byref(c)) == bb.E_INVALID
+    # the collective entries need a GPU context and an initialised group
+    with bb.Fisheye(device=None) as fe:
+        with pytest.raises(bb.BlinkyError) as ei:
+            fe.shard_init(0, 1, b"\0" * 128)
+        assert ei.value.code == bb.E_NODEVICE
+
+
 def test_frames_for_rank_partitions_exactly():
     from blinky_b200.sharding import frames_for_rank
 
