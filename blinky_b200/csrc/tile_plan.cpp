@@ -28,9 +28,9 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
     for (int tx = 0; tx < tiles_x; ++tx) {
         const int x0 = tx * kTileW, y0 = ty * kTileH;
         // collect the tile (pixels beyond the frame edge are unmapped)
-        bool any = false, one_plate = true;
+        bool any = false, one_plate = true, one_tint = true;
         int nvalid = 0;
-        uint32_t plate = 0;
+        uint32_t plate = 0, tile_tint = BLINKY_LM_TINT_NONE;
         uint32_t minx = ~0u, miny = ~0u, maxx = 0, maxy = 0;
         for (int r = 0; r < kTileH; ++r) {
             for (int c = 0; c < kTileW; ++c) {
@@ -48,6 +48,11 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
                 } else if (p != plate) {
                     one_plate = false;
                 }
+                const uint32_t tint = (e >> BLINKY_LM_TINT_SHIFT) & 7u;
+                if (tint != BLINKY_LM_TINT_NONE) {
+                    if (tile_tint == BLINKY_LM_TINT_NONE) tile_tint = tint;
+                    else if (tint != tile_tint) one_tint = false;  // forward-built maps: the tint is sticky, the texel is the last writer's
+                }
                 minx = std::min(minx, px);
                 maxx = std::max(maxx, px);
                 miny = std::min(miny, py);
@@ -63,7 +68,7 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
             row.tiles.push_back(d);
             continue;
         }
-        bool box = allow_box && one_plate;
+        bool box = allow_box && one_plate && one_tint;
         uint32_t bw = 0, bh = 0;
         if (box) {
             // TMA faults ("illegal instruction") unless the innermost coordinate is a multiple of
@@ -77,30 +82,27 @@ void plan_tile_row(const uint32_t *packed, int width, int height, int platesize,
         std::vector<uint8_t> &blk = row.blocks[static_cast<size_t>(tx)];
         if (box) {
             d.type = nvalid == kTilePixels ? TILE_BOX_FULL : TILE_BOX;
-            d.plate = static_cast<uint8_t>(plate);
+            d.plate = static_cast<uint8_t>(plate | (tile_tint << 3));
             d.box_x = static_cast<int16_t>(minx);
             d.box_y = static_cast<int16_t>(miny);
             d.box_w16 = static_cast<uint8_t>(bw / 16);
             d.box_h8 = static_cast<uint8_t>(bh / 8);
             blk.assign(kBoxBlockBytes, 0);
             uint16_t *ent = reinterpret_cast<uint16_t *>(blk.data());
-            uint8_t *tints = blk.data() + kBoxEntryBytes;
+            uint32_t *tinted = reinterpret_cast<uint32_t *>(blk.data() + kBoxEntryBytes);
             for (int lane = 0; lane < 32; ++lane) {
                 for (int i = 0; i < 32; ++i) {
                     int r, c;
                     box_lane_pixel(lane, i, &r, &c);
                     const uint32_t e = tile[static_cast<size_t>(r) * kTileW + c];
                     uint16_t v = 0;  // unmapped: offset 0 (a harmless read), not valid
-                    uint8_t t = kTintIdentity;
                     if (e & BLINKY_LM_VALID) {
                         const uint32_t rem = (e & BLINKY_LM_INDEX_MASK) % ps2;
                         const uint32_t py = rem / ps, px = rem % ps;
                         v = static_cast<uint16_t>(kBoxValid | ((py - miny) * bw + (px - minx)));
-                        const uint32_t tint = (e >> BLINKY_LM_TINT_SHIFT) & 7u;
-                        if (tint != BLINKY_LM_TINT_NONE) t = static_cast<uint8_t>(tint);
+                        if (((e >> BLINKY_LM_TINT_SHIFT) & 7u) != BLINKY_LM_TINT_NONE) tinted[lane] |= 1u << i;
                     }
                     ent[((i >> 3) * 32 + lane) * 8 + (i & 7)] = v;
-                    tints[((i >> 4) * 32 + lane) * 16 + (i & 15)] = t;
                 }
             }
             row.box_bytes += static_cast<uint64_t>(bw) * bh;

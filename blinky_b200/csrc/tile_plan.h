@@ -40,7 +40,7 @@ constexpr int kTileTypeMask = 3, kTileShapeShift = 2;
 // 16-bit entry of a BOX tile
 constexpr uint16_t kBoxValid = 0x8000;
 constexpr uint16_t kBoxOffsetMask = 0x3FFF;
-constexpr uint8_t kTintIdentity = 6;       // tint byte of an untinted pixel (row 6 of the kernel's LUT is the identity)
+constexpr uint8_t kTileTintNone = 7;       // TileDesc tint of a BOX tile without tinted pixels
 
 // Entry block of a BOX tile (kBoxBlockBytes):
 //   [4][32][8] uint16 : load k (0..3) of lane l (0..31) is the 16 bytes at (k*32 + l)*16 -> fully
@@ -48,10 +48,12 @@ constexpr uint8_t kTintIdentity = 6;       // tint byte of an untinted pixel (ro
 //                       which sits at tile row (l >> 3) + 4*(i >> 2), column 4*(l & 7) + (i & 3):
 //                       a lane owns 8 quads (4 consecutive pixels each), a warp-level access covers
 //                       4 tile rows.
-//   [2][32][16] uint8 : tint byte (0..5 = plate LUT, 6 = none) of the lane's pixel i = 16*m + j
-//                       (second index = lane); only read when the rubix overlay is on.
+//   [32] uint32       : bit i of word l = the lane's pixel i is tinted (rubix overlay).  All tinted pixels
+//                       of a BOX tile share ONE tint (TileDesc::plate bits 3-5; in inverse-built maps it is
+//                       the tile's plate, fisheye.c:1953-1958) — a tile with mixed tints is a GATHER tile —
+//                       so the kernel applies one LUT row per tile and merges by byte masks.
 constexpr int kBoxEntryBytes = kTilePixels * 2;
-constexpr int kBoxTintBytes = kTilePixels;
+constexpr int kBoxTintBytes = 32 * 4;
 constexpr int kBoxBlockBytes = kBoxEntryBytes + kBoxTintBytes;
 // Entry block of a GATHER tile: [32][32] uint32 in the packed BLINKY_LM_* format, row-major.
 constexpr int kGatherBlockBytes = kTilePixels * 4;
@@ -64,7 +66,7 @@ inline void box_lane_pixel(int lane, int i, int *row, int *col) {
 struct TileDesc {       // 16 bytes, read by the kernel
     uint32_t entry_offset;  // byte offset of the tile's entry block (= what the index-based rule gives)
     int16_t box_x, box_y;   // box origin in plate texel coordinates (may be < 0: TMA zero-fills)
-    uint8_t plate;
+    uint8_t plate;          // BOX tiles: plate (bits 0-2) | tint of the tile's tinted pixels << 3 (0-5, 7 = none tinted)
     uint8_t type;           // TileType | shape index << kTileShapeShift (BOX tiles)
     uint8_t box_w16;        // box width / 16  (1..16)
     uint8_t box_h8;         // box height / 8  (1..32)

@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // pixels of one row.  EMPTY tiles copy the background.
 // --------------------------------------------------------------------------
 constexpr int kRingMaxStages = 4;
+constexpr int kRingBarBytes = (kRingMaxStages + 1) * 8 + 8;   // mbarriers, padded to 16 bytes
+static_assert(kRingBarBytes % 16 == 0 && kBoxBlockBytes % 16 == 0, "the entry buffer is read with 128-bit loads");
 
 struct RingParams {
     const TileDesc *tiles;
@@ -205,6 +207,9 @@ struct RingParams {
     uint32_t stage_bytes, nstages;
     int width, height;
     uint32_t zero;  // always 0, but only the host knows: see stage_dep()
+    uint32_t lab;   // BLINKY_LAB builds only (make lab): bit 0 no stores, bit 1 bank-conflict-free gather offsets,
+                    // bit 2 each warp-level store covers 128 contiguous bytes, bit 3 every frame reads frame 0's
+                    // faces (L2-resident), bit 4 no box loads at all — wrong pixels, timing experiments
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -235,6 +240,20 @@ __device__ __forceinline__ void tma_load_box(uint32_t smem_dst, const CUtensorMa
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
         ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(plate), "r"(frame), "r"(bar)
         : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
     uint4 r;
@@ -274,13 +293,9 @@ struct RingTmaps {
 struct RingUnit {     // what the warp knows about one of its upcoming units (all warp-uniform)
     uint32_t ticket;  // unit index; >= nunits: none
     uint32_t tile, f0, nf;
-    uint32_t type;    // TileType
-    uint32_t dw;      // tile origin on the screen (x | y << 16)
-    // BOX units: everything a TMA issue needs, worked out once per unit
-    uint64_t tmap;    // generic address of the shape's descriptor in the parameter block
-    int bx, by, plate;
-    uint32_t bytes;
+    uint32_t dy, dz, dw;  // words 1..3 of the tile's descriptor: box origin | plate, type, box shape | screen origin
 };
+__device__ __forceinline__ uint32_t unit_type(const RingUnit &u) { return (u.dz >> 8) & kTileTypeMask; }
 
 // eight 32-bit streaming stores in ONE asm statement: all eight addresses are live at once, so the
 // stores issue back to back (with one store per statement the compiler recycled a single address
@@ -310,18 +325,20 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     const uint32_t S = p.stage_bytes, D = p.nstages;
     const uint32_t ring = smem_u32(smem_raw);
     uint8_t *tail = smem_raw + static_cast<size_t>(S) * D;
-    const uint32_t bars = smem_u32(tail);
-    uint8_t *s_lut = tail + kRingMaxStages * 8;                       // [7][256]: 6 plate LUTs + identity
-    uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + (RUBIX ? 7 * 256 : 0));
+    const uint32_t bars = smem_u32(tail);                             // kRingMaxStages stage barriers + the entry buffer's
+    const uint32_t ebar = bars + kRingMaxStages * 8;
+    const uint32_t ebuf = smem_u32(tail + kRingBarBytes);             // entry block of the next BOX unit (kBoxBlockBytes)
+    uint8_t *s_lut = tail + kRingBarBytes + kBoxBlockBytes;           // [6][256] plate LUTs
+    uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + (RUBIX ? 6 * 256 : 0));
     if (lane == 0) {
         for (uint32_t s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
+        mbar_init(ebar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (RUBIX) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
         for (uint32_t i = lane; i < 6 * 256 / 4; i += 32) dst[i] = __ldg(src + i);
-        for (uint32_t i = lane; i < 64; i += 32) dst[6 * 64 + i] = (4 * i) * 0x01010101u + 0x03020100u;
     }
     if (RGBA) {
         for (uint32_t i = lane; i < 256; i += 32) s_rgba[i] = __ldg(p.rgba + i);
@@ -335,36 +352,29 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     auto describe = [&](uint32_t ticket) {
         RingUnit u;
         u.ticket = ticket;
-        u.tile = 0; u.f0 = 0; u.nf = 0; u.type = TILE_EMPTY; u.dw = 0;
-        u.tmap = 0; u.bx = u.by = u.plate = 0; u.bytes = 0;
+        u.tile = 0; u.f0 = 0; u.nf = 0; u.dy = 0; u.dz = 0; u.dw = 0;
         if (ticket < p.nunits) {
             u.tile = ticket / p.nchunks;
             const uint32_t chunk = ticket - u.tile * p.nchunks;
             u.f0 = chunk * p.fchunk;
             u.nf = min(p.fchunk, p.nframes - u.f0);
             const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + u.tile));
-            u.type = (d.z >> 8) & kTileTypeMask;
-            u.dw = d.w;
-            u.tmap = reinterpret_cast<uint64_t>(&tm.m[(d.z >> (8 + kTileShapeShift)) & 63u]);
-            u.bx = static_cast<int16_t>(d.y & 0xffffu);
-            u.by = static_cast<int16_t>(d.y >> 16);
-            u.plate = static_cast<int>(d.z & 0xffu);
-            u.bytes = ((d.z >> 16) & 0xffu) * (d.z >> 24) * 128u;
+            u.dy = d.y; u.dz = d.z; u.dw = d.w;
         }
         return u;
     };
     auto is_box = [&](const RingUnit &u) { return u.ticket < p.nunits && u.tile < p.nbox; };
-    // entry words of a BOX unit: 4 x 128 bit (+ 2 x 128 bit of tint bytes when the overlay is on)
-    auto load_box_entries = [&](const RingUnit &u, uint4 (&e)[4], uint4 (&t)[2]) {
-        if (is_box(u)) {
-            const uint8_t *blk = p.entries + static_cast<size_t>(u.tile) * kBoxBlockBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = ldg_nc_v4(blk + (k * 32 + lane) * 16);
-            if (RUBIX) {
-                t[0] = ldg_nc_v4(blk + kBoxEntryBytes + lane * 16);
-                t[1] = ldg_nc_v4(blk + kBoxEntryBytes + (32 + lane) * 16);
-            }
+    // Entry block of a BOX unit: fetched by a bulk copy into the warp's entry buffer a whole unit before it
+    // is needed, unpacked from there into registers when the unit starts (no registers are held for it in
+    // between, and the copy does not sit on a scoreboard).  e_ticket = the unit whose block is in the
+    // buffer or on its way.
+    uint32_t e_ticket = 0xffffffffu, e_phase = 0;
+    auto fetch_entries = [&](const RingUnit &u, uint32_t dep) {
+        if (lane == 0) {
+            mbar_expect_tx(ebar, kBoxBlockBytes);
+            bulk_load(ebuf + dep, p.entries + static_cast<size_t>(u.tile) * kBoxBlockBytes, kBoxBlockBytes, ebar);
         }
+        e_ticket = u.ticket;
     };
 
     // Work distribution: the first `nstatic` units of a warp are fixed (w, w + NW, ...), the rest of the
@@ -390,12 +400,59 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     RingUnit A = describe(draw_now());
     RingUnit B = describe(draw_now());
     RingUnit C = describe(draw_now());
-    uint4 eA[4], tA[2], eB[4], tB[2];
-    load_box_entries(A, eA, tA);
+    if (is_box(A)) fetch_entries(A, 0);
 
     // ring state (warp-uniform): consume stage, issue stage, phase bit per stage, boxes in flight
     uint32_t cs = 0, is = 0, phases = 0, inflight = 0;
-    uint32_t issA = 0, issB = 0, issC = 0;  // boxes already issued for A / B / C
+    // Issue cursor: the next box of the warp's sequence — this unit's frames in order, then the frames of the
+    // next BOX units (single-frame launches, the in-engine shape, need the look-ahead to reach two units on).
+    // Its TMA operands are worked out when the cursor enters a unit, not per box.
+    //   c_unit   0/1/2 = A/B/C: the unit the cursor is in (c_left > 0) or will look at next (c_left == 0)
+    uint32_t c_unit = 0, c_left = 0, c_frame = 0, c_bytes = 0;
+    uint64_t c_tmap = 0;
+    int c_bx = 0, c_by = 0, c_plate = 0;
+    auto seat = [&]() {   // move the cursor to the first unit at or after c_unit that still has boxes to issue
+        while (c_left == 0 && c_unit < 3) {
+            // (field-wise selects: a reference chosen at run time would put the units on the stack)
+            const uint32_t ticket = c_unit == 0 ? A.ticket : c_unit == 1 ? B.ticket : C.ticket;
+            const uint32_t tile = c_unit == 0 ? A.tile : c_unit == 1 ? B.tile : C.tile;
+            if (ticket < p.nunits && tile < p.nbox) {
+                const uint32_t dy = c_unit == 0 ? A.dy : c_unit == 1 ? B.dy : C.dy;
+                const uint32_t dz = c_unit == 0 ? A.dz : c_unit == 1 ? B.dz : C.dz;
+                c_left = c_unit == 0 ? A.nf : c_unit == 1 ? B.nf : C.nf;
+                c_frame = c_unit == 0 ? A.f0 : c_unit == 1 ? B.f0 : C.f0;
+                c_tmap = reinterpret_cast<uint64_t>(&tm.m[(dz >> (8 + kTileShapeShift)) & 63u]);
+                c_bx = static_cast<int16_t>(dy & 0xffffu);
+                c_by = static_cast<int16_t>(dy >> 16);
+                c_plate = static_cast<int>(dz & 7u);
+                c_bytes = ((dz >> 16) & 0xffu) * (dz >> 24) * 128u;
+            } else {
+                ++c_unit;  // GATHER / EMPTY / no unit: nothing to stage
+            }
+        }
+    };
+    auto issue = [&](uint32_t dep) {   // precondition: c_left > 0 and a free stage
+#ifdef BLINKY_LAB
+        if (lane == 0 && !(p.lab & 16u)) {
+            const uint32_t bar = bars + 8 * is;
+            mbar_expect_tx(bar, c_bytes);
+            tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, (p.lab & 8u) ? 0 : static_cast<int>(c_frame), bar);
+        }
+#else
+        if (lane == 0) {
+            const uint32_t bar = bars + 8 * is;
+            mbar_expect_tx(bar, c_bytes);
+            tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, static_cast<int>(c_frame), bar);
+        }
+#endif
+        is = is + 1 == D ? 0 : is + 1;
+        ++inflight;
+        ++c_frame;
+        if (--c_left == 0) {
+            ++c_unit;
+            seat();
+        }
+    };
 
     while (A.ticket < p.nunits) {
         // look ahead: next ticket, B's entries.  asm volatile keeps a dynamic draw HERE, a whole unit
@@ -403,11 +460,21 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
         const bool draw_dynamic = k_next >= p.nstatic && last_good;
         uint32_t drawn = 0;
         if (draw_dynamic && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(drawn) : "l"(p.ticket) : "memory");
-        load_box_entries(B, eB, tB);
 
         const uint32_t tile_x = A.dw & 0xffffu, tile_y = A.dw >> 16;
+        const uint32_t type = unit_type(A);
+        seat();
         if (A.tile < p.nbox) {
-            // ---- unpack the lane's 32 entries once for all frames of the unit
+            while (inflight < D && c_left > 0) issue(0);
+            // ---- the lane's 32 entries, out of the entry buffer into registers once for all frames of the unit
+            if (e_ticket != A.ticket) fetch_entries(A, 0);   // first unit of the warp, or the one after a GATHER unit
+            mbar_wait(ebar, e_phase);
+            e_phase ^= 1u;
+            uint4 eA[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) eA[k] = lds_v4(ebuf + (k * 32 + lane) * 16);
+            uint32_t tintedA = 0;
+            if (RUBIX) tintedA = lds_u32(ebuf + kBoxEntryBytes + lane * 4);
             uint32_t off[32];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -418,77 +485,95 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                     off[8 * k + 2 * j + 1] = (w4[j] >> 16) & kBoxOffsetMask;
                 }
             }
-            const bool b_box = is_box(B), c_box = b_box && is_box(C);
-            // The next box of the warp's sequence goes into the free stage: this unit's next frame, else
-            // the first frames of the next units (while those are BOX units; short units — single-frame
-            // launches — need the look-ahead to reach two units on).  One issue site, operands selected.
-            auto advance = [&](uint32_t dep) {
-                const bool fromA = issA < A.nf;
-                const bool fromB = !fromA && b_box && issB < B.nf;
-                const bool fromC = !fromA && !fromB && c_box && issB >= B.nf && issC < C.nf;
-                if (!fromA && !fromB && !fromC) return;
-                const uint64_t tmap = fromA ? A.tmap : fromB ? B.tmap : C.tmap;
-                const int bx = fromA ? A.bx : fromB ? B.bx : C.bx, by = fromA ? A.by : fromB ? B.by : C.by;
-                const int plate = fromA ? A.plate : fromB ? B.plate : C.plate;
-                const uint32_t bytes = fromA ? A.bytes : fromB ? B.bytes : C.bytes;
-                const uint32_t frame = fromA ? A.f0 + issA : fromB ? B.f0 + issB : C.f0 + issC;
-                if (lane == 0) {
-                    const uint32_t bar = bars + 8 * is;
-                    mbar_expect_tx(bar, bytes);
-                    tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(tmap), bx, by, plate, static_cast<int>(frame), bar);
+#ifdef BLINKY_LAB
+            if (p.lab & 2u) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) off[i] = (lane * 4u + (i & 3) + (i >> 2) * 128u) & 1023u;
+            }
+#endif
+            // the buffer is free once its words sit in registers (same reasoning as stage_dep): refill it with
+            // the block of the next BOX unit
+            {
+                uint32_t dep = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dep |= eA[k].x | eA[k].y | eA[k].z | eA[k].w;
+                dep = (dep | tintedA) & p.zero;
+                if (is_box(B)) fetch_entries(B, dep);
+                else if (is_box(C)) fetch_entries(C, dep);
+            }
+            // rubix overlay: one LUT row for the tile, a byte mask per quad of the pixels it applies to
+            uint32_t tmask[8];
+            const uint32_t tile_tint = (A.dz >> 3) & 7u;
+            const bool tinted_tile = RUBIX && tile_tint != kTileTintNone;
+            const uint32_t lut_row = lut_base + (tile_tint & 7u) * 256u;
+            if (RUBIX) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t n = (tintedA >> (4 * q)) & 15u;
+                    // bits 0..3 -> bytes 0..3 set to 0xff
+                    tmask[q] = ((n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21)) * 255u;
                 }
-                is = is + 1 == D ? 0 : is + 1;
-                ++inflight;
-                if (fromA) ++issA;
-                else if (fromB) ++issB;
-                else ++issC;
-            };
-            while (inflight < D && (issA < A.nf || (b_box && issB < B.nf) || (c_box && issC < C.nf))) advance(0);
+            }
             // pixels of quad q (0..7): row (lane>>3) + 4q, columns 4*(lane&7) .. +3
             const uint32_t qx = tile_x + 4u * (lane & 7u), qy = tile_y + (lane >> 3);
             const size_t opx = RGBA ? 4 : 1;
-            uint8_t *out0 = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0) * p.out_stride + (static_cast<size_t>(qy) * width + qx) * opx;
-            const size_t row4 = static_cast<size_t>(width) * 4u * opx;   // four screen rows
+            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0) * p.out_stride + (static_cast<size_t>(qy) * width + qx) * opx;
+            const uint32_t row4 = width * 4u * static_cast<uint32_t>(opx);   // four screen rows, bytes
 
             // one frame: wait for its box, 32 byte loads from shared memory, pack, hand the stage on
-            auto gather_frame = [&](uint32_t (&b)[32], uint32_t (&w)[8]) {
+            auto gather_frame = [&](uint32_t (&w)[8]) {
+#ifdef BLINKY_LAB
+                if (!(p.lab & 16u))
+#endif
                 mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
                 const uint32_t base = ring + cs * S;
+                uint32_t b[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) b[i] = lds_u8(base + off[i]);
-                if (RUBIX) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint4 &tv = tA[i >> 4];
-                        const uint32_t tw = ((i >> 2) & 3) == 0 ? tv.x : ((i >> 2) & 3) == 1 ? tv.y : ((i >> 2) & 3) == 2 ? tv.z : tv.w;
-                        // (tint byte << 8) + pixel value indexes the [7][256] LUT
-                        b[i] = lds_u8(lut_base + __byte_perm(tw, 0, 0x4404 | ((i & 3) << 4)) + b[i]);
-                    }
-                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) w[q] = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
                 phases ^= 1u << cs;
                 cs = cs + 1 == D ? 0 : cs + 1;
                 --inflight;
-                advance(stage_dep(w, p.zero));
+                const uint32_t dep = stage_dep(w, p.zero);
+                if (tinted_tile) {
+                    // the tile's LUT row applied to every pixel, merged where the pixel is tinted
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) b[i] = lds_u8(lut_row + b[i]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t t = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+                        w[q] = (t & tmask[q]) | (w[q] & ~tmask[q]);
+                    }
+                }
+                if (c_left > 0) issue(dep);
+            };
+            auto store_rgba = [&](uint8_t *dst, uint32_t v) {
+                st_stream_v4(reinterpret_cast<uint4 *>(dst), make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
             };
 
-            if (A.type == TILE_BOX_FULL) {
+            if (type == TILE_BOX_FULL) {
                 for (uint32_t f = 0; f < A.nf; ++f) {
-                    uint32_t b[32], w[8];
-                    gather_frame(b, w);
-                    uint8_t *o = out0 + static_cast<size_t>(f) * p.out_stride;
+                    uint32_t w[8];
+                    gather_frame(w);
                     if (RGBA) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            st_stream_v4(reinterpret_cast<uint4 *>(o + q * row4),
-                                         make_uint4(s_rgba[b[4 * q]], s_rgba[b[4 * q + 1]], s_rgba[b[4 * q + 2]], s_rgba[b[4 * q + 3]]));
+                        for (int q = 0; q < 8; ++q) store_rgba(o + static_cast<size_t>(static_cast<uint32_t>(q) * row4), w[q]);
                     } else {
                         uint64_t a[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) a[q] = reinterpret_cast<uint64_t>(o + q * row4);
+                        for (int q = 0; q < 8; ++q) a[q] = reinterpret_cast<uint64_t>(o) + static_cast<uint64_t>(static_cast<uint32_t>(q) * row4);
+#ifdef BLINKY_LAB
+                        if (p.lab & 4u) {
+                            uint8_t *fb = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride + static_cast<size_t>(A.tile) * 1024u;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) a[q] = reinterpret_cast<uint64_t>(fb + q * 128 + lane * 4u);
+                        }
+                        if (!(p.lab & 1u) || w[0] == 0x12345679u)
+#endif
                         st_stream_u32x8(a, w);
                     }
+                    o += p.out_stride;
                 }
             } else {
                 // partly mapped tile, or one that hangs over the frame edge: per quad a byte mask of the
@@ -512,17 +597,17 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                     }
                 }
                 for (uint32_t f = 0; f < A.nf; ++f) {
-                    uint32_t b[32], w[8];
-                    gather_frame(b, w);
-                    uint8_t *o = out0 + static_cast<size_t>(f) * p.out_stride;
+                    uint32_t w[8];
+                    gather_frame(w);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (!((store_mask >> q) & 1u)) continue;
                         const uint32_t v = (w[q] & vmask[q]) | bgw[q];
-                        if (RGBA) st_stream_v4(reinterpret_cast<uint4 *>(o + q * row4),
-                                               make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
-                        else st_stream_u32(reinterpret_cast<uint32_t *>(o + q * row4), v);
+                        uint8_t *dst = o + static_cast<size_t>(static_cast<uint32_t>(q) * row4);
+                        if (RGBA) store_rgba(dst, v);
+                        else st_stream_u32(reinterpret_cast<uint32_t *>(dst), v);
                     }
+                    o += p.out_stride;
                 }
             }
         } else if (A.tile < p.nbox + p.ngather) {
@@ -554,12 +639,8 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                         if (e[r] & BLINKY_LM_VALID) v[r] = ld_face(faces + (e[r] & BLINKY_LM_INDEX_MASK));
                     }
                 };
-                uint32_t v[32];
-                gather_frame(A.f0, v);
-                for (uint32_t f = 0; f < A.nf; ++f) {
-                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(A.f0 + f) * p.out_stride;
-                    uint32_t vn[32];
-                    if (f + 1 < A.nf) gather_frame(A.f0 + f + 1, vn);
+                auto store_frame = [&](uint32_t frame, const uint32_t (&v)[32]) {
+                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         if (static_cast<uint32_t>(r) >= rows) break;
@@ -572,8 +653,21 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                         if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[bv];
                         else out_frame[pix] = static_cast<uint8_t>(bv);
                     }
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) v[r] = vn[r];
+                };
+                // two value sets in turn (every read of a set follows its write in the same block: a set read
+                // before it is written in an iteration would be live around the whole unit loop)
+                uint32_t v0[32];
+                gather_frame(A.f0, v0);
+                for (uint32_t f = 0; f < A.nf; f += 2) {
+                    if (f + 1 < A.nf) {
+                        uint32_t v1[32];
+                        gather_frame(A.f0 + f + 1, v1);
+                        store_frame(A.f0 + f, v0);
+                        if (f + 2 < A.nf) gather_frame(A.f0 + f + 2, v0);
+                        store_frame(A.f0 + f + 1, v1);
+                    } else {
+                        store_frame(A.f0 + f, v0);
+                    }
                 }
             }
         } else {
@@ -595,7 +689,7 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                 }
             }
         }
-        // rotate: A <- B <- C <- the ticket drawn above
+        // rotate: A <- B <- C <- the ticket drawn above; the cursor moves with its unit
         uint32_t next_ticket = 0xffffffffu;
         if (k_next < p.nstatic) next_ticket = blockIdx.x + k_next * NW;
         else if (draw_dynamic) next_ticket = p.nstatic * NW + (__shfl_sync(0xffffffffu, drawn, 0) - p.ticket_base);
@@ -604,13 +698,7 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
         A = B;
         B = C;
         C = describe(next_ticket);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) eA[k] = eB[k];
-        tA[0] = tB[0];
-        tA[1] = tB[1];
-        issA = issB;
-        issB = issC;
-        issC = 0;
+        c_unit = c_unit > 0 ? c_unit - 1 : 0;
     }
 }
 
@@ -786,7 +874,6 @@ WarpDevice::WarpDevice(int device) : device_(device) {
     if (const char *e = getenv("BLINKY_RING_CTAS")) ring_ctas_cap_ = atoi(e);
     if (const char *e = getenv("BLINKY_FCHUNK")) fchunk_ = atoi(e);
     if (const char *e = getenv("BLINKY_SPLIT_PERCENT")) split_percent_ = atoi(e);
-    if (const char *e = getenv("BLINKY_RING_WARPS")) ring_minb_ = atoi(e);  // 12 (168 registers), 14 (144) or 16 (128) warps per SM
     if (const char *e = getenv("BLINKY_STATIC_PCT")) static_pct_ = std::max(0, std::min(100, atoi(e)));
     if (const char *e = getenv("BLINKY_L2_PROMOTION")) l2_promotion_ = atoi(e) & 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B
     cudaStream_t s;
@@ -979,7 +1066,14 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (size_t si = 0; si < shapes_.size() && si < static_cast<size_t>(kMaxShapes); ++si) {
         const uint32_t w16 = shapes_[si] >> 8, h8 = shapes_[si] & 0xff;
-        const cuuint32_t box[4] = {w16 * 16, h8 * 8, 1, 1};
+        cuuint32_t box[4] = {w16 * 16, h8 * 8, 1, 1};
+#ifdef BLINKY_LAB
+        // timing experiment: the same bytes as wider, flatter boxes (fewer TMA rows; wrong texels)
+        if (const char *e = getenv("BLINKY_LAB_FLAT")) {
+            for (int k = atoi(e); k > 1; k /= 2)
+                if (box[0] * 2 <= 256 && box[1] % 2 == 0) box[0] *= 2, box[1] /= 2;
+        }
+#endif
         CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
             &t->table.m[si], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(d_faces), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, static_cast<CUtensorMapL2promotion>(l2_promotion_), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -994,28 +1088,29 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
     return t;
 }
 
-// MINB = warps per SM the register allocation is sized for (168 registers at 12, 128 at 16)
-template <bool RUBIX, bool RGBA, int MINB>
+// kRingWarps = warps (one-warp CTAs) per SM the ring kernel's register allocation is sized for: 65536 / (32 x 12)
+// = 170 registers per thread.  (14 and 16 warps per SM with 144 / 128 registers were measured: slower, spills.)
+constexpr int kRingWarps = 12;
+
+template <bool RUBIX, bool RGBA>
 static cudaError_t ring_config(size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA, kRingWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA, MINB>, 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA, kRingWarps>, 32, smem);
 }
 
-template <int MINB>
 static cudaError_t ring_config_v(bool rubix, bool rgba, size_t smem, int *n) {
-    return rubix && rgba ? ring_config<true, true, MINB>(smem, n)
-           : rubix       ? ring_config<true, false, MINB>(smem, n)
-           : rgba        ? ring_config<false, true, MINB>(smem, n)
-                         : ring_config<false, false, MINB>(smem, n);
+    return rubix && rgba ? ring_config<true, true>(smem, n)
+           : rubix       ? ring_config<true, false>(smem, n)
+           : rgba        ? ring_config<false, true>(smem, n)
+                         : ring_config<false, false>(smem, n);
 }
 
-template <int MINB>
 static void ring_launch_v(bool rubix, bool rgba, uint32_t grid, size_t smem, cudaStream_t st, const RingParams &p, const RingTmaps &tm) {
-    if (rubix && rgba) warp_ring_kernel<true, true, MINB><<<grid, 32, smem, st>>>(p, tm);
-    else if (rubix) warp_ring_kernel<true, false, MINB><<<grid, 32, smem, st>>>(p, tm);
-    else if (rgba) warp_ring_kernel<false, true, MINB><<<grid, 32, smem, st>>>(p, tm);
-    else warp_ring_kernel<false, false, MINB><<<grid, 32, smem, st>>>(p, tm);
+    if (rubix && rgba) warp_ring_kernel<true, true, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
+    else if (rubix) warp_ring_kernel<true, false, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
+    else if (rgba) warp_ring_kernel<false, true, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
+    else warp_ring_kernel<false, false, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
 }
 
 bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
@@ -1045,6 +1140,8 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     p.width = width_;
     p.height = height_;
     p.zero = 0;
+    p.lab = 0;
+    if (const char *e = getenv("BLINKY_LAB")) p.lab = static_cast<uint32_t>(atoi(e));
     const bool rubix = rubix_;
     const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
     // Tiles [0, nbox) are BOX tiles.  A few GATHER/EMPTY tiles ride along in the ring kernel (one launch,
@@ -1058,10 +1155,10 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     // stage per unit and want one more box in flight
     p.nstages = ring_stages_ > 0 ? static_cast<uint32_t>(ring_stages_) : (p.stage_bytes <= 4096 || (nframes == 1 && p.stage_bytes <= 8192) ? 3u : 2u);
     if (p.nstages > static_cast<uint32_t>(kRingMaxStages)) p.nstages = kRingMaxStages;
-    const size_t smem = static_cast<size_t>(p.stage_bytes) * p.nstages + kRingMaxStages * 8 + (rubix ? 7 * 256 : 0) + (rgba ? 1024 : 0);
+    const size_t smem = static_cast<size_t>(p.stage_bytes) * p.nstages + kRingBarBytes + kBoxBlockBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
     if (ring_ctas_per_sm_[vi] == 0 || ring_smem_[vi] != smem) {
         int n = 0;
-        cudaError_t e = ring_minb_ == 16 ? ring_config_v<16>(rubix, rgba, smem, &n) : ring_minb_ == 14 ? ring_config_v<14>(rubix, rgba, smem, &n) : ring_config_v<12>(rubix, rgba, smem, &n);
+        cudaError_t e = ring_config_v(rubix, rgba, smem, &n);
         if (e != cudaSuccess) return fail("ring kernel configuration (shared memory / occupancy)", e);
         if (n < 1) {
             err_ = "ring kernel does not fit on an SM";
@@ -1129,14 +1226,15 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
         }
         tc->base += good + drawers;
 
-        if (ring_minb_ == 16) ring_launch_v<16>(rubix, rgba, grid, smem, st, p, *tm);
-        else if (ring_minb_ == 14) ring_launch_v<14>(rubix, rgba, grid, smem, st, p, *tm);
-        else ring_launch_v<12>(rubix, rgba, grid, smem, st, p, *tm);
+        ring_launch_v(rubix, rgba, grid, smem, st, p, *tm);
         ++launches_;
         nbuf = snprintf(buf, sizeof buf, "warp_ring_kernel<rubix=%d,rgba=%d> grid=%u block=32 (%d warps/SM, %u-stage TMA ring of %u B, %u frames/unit, %u units)", rubix,
                         rgba, grid, ctas, p.nstages, p.stage_bytes, fchunk, p.nunits);
     }
-    const uint32_t nother = ntiles_ - ring_tiles;
+    uint32_t nother = ntiles_ - ring_tiles;
+#ifdef BLINKY_LAB
+    if (getenv("BLINKY_LAB_NOK3")) nother = 0;  // time the ring kernel alone
+#endif
     if (nother > 0) {
         dim3 g2(nother, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
         if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);

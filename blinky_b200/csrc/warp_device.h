@@ -106,7 +106,6 @@ private:
     uint8_t *d_entries_ = nullptr;
     uint32_t ntiles_ = 0, nbox_tiles_ = 0, ngather_tiles_ = 0;
     int stage_bytes_ = 0;                // largest staged box of the plan
-    int ring_minb_ = 12;                 // warps per SM the ring kernel's registers are sized for (BLINKY_RING_WARPS: 12, 14, 16)
     int static_pct_ = 85;                // share of the ring kernel's units scheduled statically (BLINKY_STATIC_PCT)
     int l2_promotion_ = 0;               // CUtensorMapL2promotion of the box descriptors (BLINKY_L2_PROMOTION)
     int split_percent_ = 12;             // GATHER+EMPTY share of tiles above which they get their own kernel (BLINKY_SPLIT_PERCENT)

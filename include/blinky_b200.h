@@ -280,13 +280,14 @@ int blinky_warp_device_rgba(blinky_ctx *ctx, const void *d_faces, size_t face_st
  * (tile counts per class, staged bytes per pixel); "" before a build */
 const char *blinky_plan_summary(blinky_ctx *ctx);
 /* The tile plan the kernels read: 16-byte tile descriptors
- * {u32 entry_offset; i16 box_x, box_y; u8 plate, type (0 empty, 1 box, 2 gather, 3 box fully mapped),
- * box_w/16, box_h/8; u16 px, py} — the upper six bits of `type` are the index of the box shape (one TMA
- * descriptor per shape, at most 64) — ordered BOX tiles, GATHER tiles, EMPTY tiles, and the entry blocks in
- * the same order, fixed sizes: BOX 3072 bytes = [4][32 lanes][8] uint16 {bit 15 valid, bits 0-13 offset
- * inside the box} in the ring kernel's lane order (lane l, entry i -> tile row (l>>3) + 4*(i>>2), column
- * 4*(l&7) + (i&3)) followed by [2][32 lanes][16] tint bytes (0-5 plate, 6 none); GATHER 4096 bytes =
- * [32][32] packed 32-bit lensmap entries.  Pass NULL buffers to query the sizes.  Works on CPU-only contexts;
+ * {u32 entry_offset; i16 box_x, box_y; u8 plate (bits 0-2) | tile tint << 3 (0-5, 7 = no pixel tinted),
+ * type (0 empty, 1 box, 2 gather, 3 box fully mapped), box_w/16, box_h/8; u16 px, py} — the upper six bits of
+ * `type` are the index of the box shape (one TMA descriptor per shape, at most 64) — ordered BOX tiles, GATHER
+ * tiles, EMPTY tiles, and the entry blocks in the same order, fixed sizes: BOX 2176 bytes = [4][32 lanes][8]
+ * uint16 {bit 15 valid, bits 0-13 offset inside the box} in the ring kernel's lane order (lane l, entry i ->
+ * tile row (l>>3) + 4*(i>>2), column 4*(l&7) + (i&3)) followed by [32 lanes] uint32 tint flags (bit i: the
+ * lane's pixel i carries the tile's tint; tiles whose tinted pixels disagree are GATHER tiles); GATHER 4096
+ * bytes = [32][32] packed 32-bit lensmap entries.  Pass NULL buffers to query the sizes.  Works on CPU-only contexts;
  * the tests interpret the plan on the CPU to pin this layout (tests/test_tile_plan.py). */
 int blinky_get_tile_plan(blinky_ctx *ctx, void *tiles_out, size_t tiles_cap, void *entries_out, size_t entries_cap, size_t *ntiles,
                          size_t *entry_bytes);

@@ -56,15 +56,17 @@ def run(work, env, frames=16, iters=8, cold=False, kernel=0):
             fe.warp(faces, out, nframes=nf, stream=st)
         torch.cuda.synchronize()
         times = []
+        reps = 1 if cold else 10   # back-to-back launches between the events (as bench.py times them): no launch latency in the number
         for _ in range(iters):
             if cold:
                 _flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fe.warp(faces, out, nframes=nf, stream=st)
+            for _ in range(reps):
+                fe.warp(faces, out, nframes=nf, stream=st)
             e1.record()
             torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1) * 1e-3)
+            times.append(e0.elapsed_time(e1) * 1e-3 / reps)
         t = float(np.median(times))
         print(json.dumps(dict(work=work, env=env, frames=nf, cold=cold, us_per_frame=round(t * 1e6 / nf, 2), min_us=round(min(times) * 1e6 / nf, 2),
                               tpx_s=round(W * H * nf / t / 1e12, 3), kernel=fe.last_kernel, plan=fe.plan_summary)), flush=True)

@@ -1,7 +1,7 @@
 """The tile plan is the lensmap's layout in HBM — what the warp kernels actually read.
 Here it is interpreted on the CPU, tile by tile the way the ring kernel does (source box cut out of the
 faces with zero fill outside the plate; 16-bit entries in the kernel's lane order indexing into the
-box, tint bytes in their own block; 32-bit entries for gather tiles; background for empty tiles and
+box, one tint per tile applied where the tile's flag words say so; 32-bit entries for gather tiles; background for empty tiles and
 unmapped pixels; entry blocks addressed by tile index alone), and the result must be the reference's
 render_lensmap.  This pins the planner and the layout contract without a GPU."""
 import numpy as np
@@ -10,7 +10,7 @@ import pytest
 EMPTY, BOX, GATHER, BOX_FULL = 0, 1, 2, 3
 
 
-BOX_BLOCK, GATHER_BLOCK = 2048 + 1024, 4096
+BOX_BLOCK, GATHER_BLOCK = 2048 + 128, 4096
 
 
 def lane_pixel(lane, i):
@@ -45,7 +45,7 @@ def render_from_plan(fe, faces, palmaps, bg, rubix, max_box=8192):
             shapes.setdefault(shape, (int(t["box_w16"]), int(t["box_h8"])))
             assert shapes[shape] == (int(t["box_w16"]), int(t["box_h8"])) and shape < 64
             bw, bh = int(t["box_w16"]) * 16, int(t["box_h8"]) * 8
-            bx, by, plate = int(t["box_x"]), int(t["box_y"]), int(t["plate"])
+            bx, by, plate, tile_tint = int(t["box_x"]), int(t["box_y"]), int(t["plate"]) & 7, (int(t["plate"]) >> 3) & 7
             assert 16 <= bw <= 256 and 8 <= bh <= 256 and bw * bh <= max_box and bx % 16 == 0  # TMA constraints
             assert int(t["entry_offset"]) == n * BOX_BLOCK
             box = np.zeros((bh, bw), np.uint8)  # TMA zero-fills what lies outside the tensor
@@ -55,13 +55,14 @@ def render_from_plan(fe, faces, palmaps, bg, rubix, max_box=8192):
                 box[sy0 - by:sy1 - by, sx0 - bx:sx1 - bx] = faces[plate, sy0:sy1, sx0:sx1]
             blk = entries[n * BOX_BLOCK:(n + 1) * BOX_BLOCK]
             ent = blk[:2048].view("<u2").reshape(4, 32, 8)     # [load k][lane][j]: pixel i = 8k + j
-            tnt = blk[2048:].reshape(2, 32, 16)                # [m][lane][j]: pixel i = 16m + j
+            flags = blk[2048:].view("<u4")                     # [lane]: bit i = the lane's pixel i carries the tile's tint
+            assert tile_tint <= 5 or (tile_tint == 7 and not flags.any())
             e = np.zeros((32, 32), np.uint16)
             tint = np.zeros((32, 32), np.int64)
             for i in range(32):
                 r, c = lane_pixel(lanes, i)
                 e[r, c] = ent[i >> 3, lanes, i & 7]
-                tint[r, c] = tnt[i >> 4, lanes, i & 15]
+                tint[r, c] = np.where((flags >> i) & 1, tile_tint, 6)
             valid = (e & 0x8000) != 0
             if ty == BOX_FULL:
                 assert valid.all() and ys == 32 and xs == 32
