@@ -181,12 +181,14 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // There is no producer warp, no cross-warp barrier and no per-pixel entry traffic per frame:
 // round 1's kernel was bound by the serial per-item work of its producer thread (5.2 us/frame
 // with every load and store removed, profiles/r2_c1_k2lab.txt).
-// GATHER tiles (plate seams, singular points, boxes too large to stage) carry 32-bit entries and
-// read the globe directly: lane = column, so one warp-level load covers 32 consecutive screen
-// pixels of one row.  EMPTY tiles copy the background.
+// EMPTY tiles copy the background.  GATHER tiles (plate seams, singular points, boxes too large to
+// stage) are not this kernel's: their direct global gathers need ~130 registers per thread for the
+// loads in flight, which capped the whole kernel at 12 warps per SM while the BOX path needs 100
+// (measured: time = 2.8 us + 19.8 us / warps-per-SM per 4K frame).  They go to the gather kernel K3,
+// launched on a second stream so that it runs beside this kernel.
 // --------------------------------------------------------------------------
-constexpr int kRingMaxStages = 4;
-constexpr int kRingBarBytes = (kRingMaxStages + 1) * 8 + 8;   // mbarriers, padded to 16 bytes
+constexpr int kRingBoxes = 6;                                 // boxes in flight per warp at most (one mbarrier each)
+constexpr int kRingBarBytes = (kRingBoxes + 1) * 8 + 8;       // mbarriers (+ the entry buffer's), padded to 16 bytes
 static_assert(kRingBarBytes % 16 == 0 && kBoxBlockBytes % 16 == 0, "the entry buffer is read with 128-bit loads");
 
 struct RingParams {
@@ -204,9 +206,12 @@ struct RingParams {
     uint32_t nstatic;       // units per warp that are assigned statically (warp w owns w, w+NW, ...) before it draws tickets
     uint32_t nbox, ngather, ntiles;
     uint32_t nframes, fchunk, nchunks, nunits;
-    uint32_t stage_bytes, nstages;
+    uint32_t ring_bytes;    // the warp's staging ring: boxes are packed into it one behind the other (multiple of 128)
+    uint32_t max_inflight;  // boxes a warp keeps in flight at most (<= kRingBoxes)
+    uint32_t ring_grid;     // CTAs [0, ring_grid) are ring warps, the CTAs behind them take one gather item each
     int width, height;
     uint32_t zero;  // always 0, but only the host knows: see stage_dep()
+    uint32_t lab_bytes;  // (lab bit 5) bytes of box shape 0
     uint32_t lab;   // BLINKY_LAB builds only (make lab): bit 0 no stores, bit 1 bank-conflict-free gather offsets,
                     // bit 2 each warp-level store covers 128 contiguous bytes, bit 3 every frame reads frame 0's
                     // faces (L2-resident), bit 4 no box loads at all — wrong pixels, timing experiments
@@ -315,6 +320,62 @@ __device__ __forceinline__ void st_stream_u32x8(const uint64_t (&a)[8], const ui
         : "memory");
 }
 
+// ---- gather role of the ring kernel's launch ---------------------------------------------------------------
+// GATHER tiles (plate seams, singular points, boxes too large to stage) read the globe directly: 32-bit
+// entries, lane = column, so one warp-level load covers 32 consecutive screen pixels of one row.  They are
+// bound by load latency, so they get plain parallelism: one extra one-warp CTA per (tile, 8 of its rows, 4
+// frames) behind the ring CTAs in the same grid.  The launch leaves shared memory for two of them per SM next
+// to the resident ring warps, so this work runs beside the ring warps from the start and fills the slots they
+// vacate at the end — as a separate kernel behind the ring kernel it cost 0.7 us per 4K panini frame for 3.5 %
+// of the tiles.
+constexpr int kGatherRows = 8, kGatherFrames = 4;
+
+template <bool RUBIX, bool RGBA>
+__device__ __forceinline__ void gather_item(const RingParams &p, uint32_t item, uint32_t lane) {
+    const uint32_t nfg = (p.nframes + kGatherFrames - 1) / kGatherFrames;
+    const uint32_t fg = item % nfg, rest = item / nfg;
+    const uint32_t rg = rest % (kTileH / kGatherRows), gt = rest / (kTileH / kGatherRows);
+    const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.nbox + gt));
+    const uint32_t tile_x = d.w & 0xffffu, tile_y = (d.w >> 16) + rg * kGatherRows;
+    const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
+    const uint32_t f0 = fg * kGatherFrames, f1 = min(f0 + kGatherFrames, p.nframes);
+    const uint32_t x = tile_x + lane;
+    const uint32_t *__restrict__ ent32 = reinterpret_cast<const uint32_t *>(p.entries + d.x) + rg * kGatherRows * kTileW;
+    uint32_t e[kGatherRows];
+#pragma unroll
+    for (int j = 0; j < kGatherRows; ++j) e[j] = __ldg(ent32 + j * kTileW + lane);
+    if (x >= width) return;
+    uint32_t v[kGatherFrames][kGatherRows];
+#pragma unroll
+    for (int g = 0; g < kGatherFrames; ++g) {
+        const uint32_t f = f0 + g;
+        const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(f < f1 ? f : f0) * p.face_stride;
+#pragma unroll
+        for (int j = 0; j < kGatherRows; ++j) {
+            v[g][j] = 0x100u;   // "take the background"
+            if (e[j] & BLINKY_LM_VALID) v[g][j] = ld_face(faces + (e[j] & BLINKY_LM_INDEX_MASK));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kGatherRows; ++j) {
+        const uint32_t y = tile_y + j;
+        if (y >= height) break;
+        const size_t pix = static_cast<size_t>(y) * width + x;
+        uint32_t bgv = 0, t = BLINKY_LM_TINT_NONE;
+        if (!(e[j] & BLINKY_LM_VALID)) bgv = __ldg(p.bg + pix);
+        else if (RUBIX) t = (e[j] >> BLINKY_LM_TINT_SHIFT) & 7u;
+#pragma unroll
+        for (int g = 0; g < kGatherFrames; ++g) {
+            if (f0 + g >= f1) break;
+            uint32_t b = v[g][j] & 0x100u ? bgv : v[g][j];
+            if (RUBIX && t != BLINKY_LM_TINT_NONE) b = __ldg(p.lut + t * 256 + b);
+            uint8_t *o = static_cast<uint8_t *>(p.out) + static_cast<size_t>(f0 + g) * p.out_stride;
+            if (RGBA) reinterpret_cast<uint32_t *>(o)[pix] = __ldg(p.rgba + b);
+            else o[pix] = static_cast<uint8_t>(b);
+        }
+    }
+}
+
 // MINB: warps (= CTAs) per SM the register allocation is sized for
 template <bool RUBIX, bool RGBA, int MINB>
 __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_constant__ RingParams p, const __grid_constant__ RingTmaps tm) {
@@ -322,16 +383,20 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     // XOR with a parameter that is always zero: keeps ptxas from re-reading the special register
     // (S2R, tens of cycles) at every `lane == 0` test instead of holding the lane number in a register
     const uint32_t lane = threadIdx.x ^ p.zero;
-    const uint32_t S = p.stage_bytes, D = p.nstages;
+    if (blockIdx.x >= p.ring_grid) {   // the CTAs behind the ring warps: one gather item each
+        gather_item<RUBIX, RGBA>(p, blockIdx.x - p.ring_grid, lane);
+        return;
+    }
+    const uint32_t R = p.ring_bytes;
     const uint32_t ring = smem_u32(smem_raw);
-    uint8_t *tail = smem_raw + static_cast<size_t>(S) * D;
-    const uint32_t bars = smem_u32(tail);                             // kRingMaxStages stage barriers + the entry buffer's
-    const uint32_t ebar = bars + kRingMaxStages * 8;
+    uint8_t *tail = smem_raw + static_cast<size_t>(R);
+    const uint32_t bars = smem_u32(tail);                             // kRingBoxes box barriers + the entry buffer's
+    const uint32_t ebar = bars + kRingBoxes * 8;
     const uint32_t ebuf = smem_u32(tail + kRingBarBytes);             // entry block of the next BOX unit (kBoxBlockBytes)
     uint8_t *s_lut = tail + kRingBarBytes + kBoxBlockBytes;           // [6][256] plate LUTs
     uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + (RUBIX ? 6 * 256 : 0));
     if (lane == 0) {
-        for (uint32_t s = 0; s < D; ++s) mbar_init(bars + 8 * s, 1);
+        for (uint32_t s = 0; s < kRingBoxes; ++s) mbar_init(bars + 8 * s, 1);
         mbar_init(ebar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -346,7 +411,7 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     __syncwarp();
     const uint32_t lut_base = smem_u32(s_lut);
 
-    const uint32_t NW = gridDim.x;
+    const uint32_t NW = p.ring_grid;
     const uint32_t width = static_cast<uint32_t>(p.width), height = static_cast<uint32_t>(p.height);
 
     auto describe = [&](uint32_t ticket) {
@@ -358,7 +423,9 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
             const uint32_t chunk = ticket - u.tile * p.nchunks;
             u.f0 = chunk * p.fchunk;
             u.nf = min(p.fchunk, p.nframes - u.f0);
-            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + u.tile));
+            // the ring kernel's tiles: the plan's BOX tiles [0, nbox), then its EMPTY tiles (the GATHER tiles in between
+            // belong to the gather kernel)
+            const uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tiles + (u.tile < p.nbox ? u.tile : u.tile + p.ngather)));
             u.dy = d.y; u.dz = d.z; u.dw = d.w;
         }
         return u;
@@ -402,8 +469,18 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     RingUnit C = describe(draw_now());
     if (is_box(A)) fetch_entries(A, 0);
 
-    // ring state (warp-uniform): consume stage, issue stage, phase bit per stage, boxes in flight
-    uint32_t cs = 0, is = 0, phases = 0, inflight = 0;
+    // Ring state (warp-uniform).  The ring is a byte FIFO: a box goes behind the previous one, or at offset 0 when
+    // it would run over the end — a rule the consuming side repeats with the same box sizes, so no positions are
+    // passed along.  Small boxes therefore cost small space, and a warp with 2 KB boxes has four in flight where
+    // fixed stages sized for the plan's largest box held two.
+    //   ipos   where the next box goes        cpos   end of the last consumed box (everything in flight lies
+    //   is/cs  barrier slot of the next box to issue / to consume, phases: their parity bits     behind it)
+    uint32_t cs = 0, is = 0, phases = 0, inflight = 0, ipos = 0, cpos = 0;
+    auto room_for = [&](uint32_t n) {   // can a box of n bytes be placed now?
+        if (inflight == 0) return true;                     // (n <= R: the planner caps boxes at the ring size)
+        if (ipos > cpos) return ipos + n <= R || n <= cpos; // in flight: [cpos, ipos)
+        return ipos + n <= cpos;                            // in flight: [cpos, R) and [0, ipos)
+    };
     // Issue cursor: the next box of the warp's sequence — this unit's frames in order, then the frames of the
     // next BOX units (single-frame launches, the in-engine shape, need the look-ahead to reach two units on).
     // Its TMA operands are worked out when the cursor enters a unit, not per box.
@@ -426,26 +503,36 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                 c_by = static_cast<int16_t>(dy >> 16);
                 c_plate = static_cast<int>(dz & 7u);
                 c_bytes = ((dz >> 16) & 0xffu) * (dz >> 24) * 128u;
+#ifdef BLINKY_LAB
+                if (p.lab & 32u) {   // every box through ONE descriptor (shape 0): is the TMA unit's descriptor cache the limit?
+                    c_tmap = reinterpret_cast<uint64_t>(&tm.m[0]);
+                    c_bytes = p.lab_bytes;
+                }
+#endif
             } else {
                 ++c_unit;  // GATHER / EMPTY / no unit: nothing to stage
             }
         }
     };
-    auto issue = [&](uint32_t dep) {   // precondition: c_left > 0 and a free stage
+    auto can_issue = [&]() { return c_left > 0 && inflight < p.max_inflight && room_for(c_bytes); };
+    auto issue = [&](uint32_t dep) {   // precondition: can_issue()
+        if (inflight == 0) ipos = cpos = 0;   // (an empty ring restarts at the front: keeps "everything in flight lies behind cpos" true)
+        if (ipos + c_bytes > R) ipos = 0;
 #ifdef BLINKY_LAB
         if (lane == 0 && !(p.lab & 16u)) {
             const uint32_t bar = bars + 8 * is;
             mbar_expect_tx(bar, c_bytes);
-            tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, (p.lab & 8u) ? 0 : static_cast<int>(c_frame), bar);
+            tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, (p.lab & 8u) ? 0 : static_cast<int>(c_frame), bar);
         }
 #else
         if (lane == 0) {
             const uint32_t bar = bars + 8 * is;
             mbar_expect_tx(bar, c_bytes);
-            tma_load_box(ring + is * S + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, static_cast<int>(c_frame), bar);
+            tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, static_cast<int>(c_frame), bar);
         }
 #endif
-        is = is + 1 == D ? 0 : is + 1;
+        ipos += c_bytes;
+        is = is + 1 == kRingBoxes ? 0 : is + 1;
         ++inflight;
         ++c_frame;
         if (--c_left == 0) {
@@ -465,7 +552,11 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
         const uint32_t type = unit_type(A);
         seat();
         if (A.tile < p.nbox) {
-            while (inflight < D && c_left > 0) issue(0);
+            while (can_issue()) issue(0);
+            uint32_t a_bytes = ((A.dz >> 16) & 0xffu) * (A.dz >> 24) * 128u;   // size of this unit's boxes
+#ifdef BLINKY_LAB
+            if (p.lab & 32u) a_bytes = p.lab_bytes;
+#endif
             // ---- the lane's 32 entries, out of the entry buffer into registers once for all frames of the unit
             if (e_ticket != A.ticket) fetch_entries(A, 0);   // first unit of the warp, or the one after a GATHER unit
             mbar_wait(ebar, e_phase);
@@ -526,14 +617,16 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                 if (!(p.lab & 16u))
 #endif
                 mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
-                const uint32_t base = ring + cs * S;
+                if (cpos + a_bytes > R) cpos = 0;
+                const uint32_t base = ring + cpos;
                 uint32_t b[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) b[i] = lds_u8(base + off[i]);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) w[q] = pack4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
                 phases ^= 1u << cs;
-                cs = cs + 1 == D ? 0 : cs + 1;
+                cs = cs + 1 == kRingBoxes ? 0 : cs + 1;
+                cpos += a_bytes;
                 --inflight;
                 const uint32_t dep = stage_dep(w, p.zero);
                 if (tinted_tile) {
@@ -546,7 +639,7 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                         w[q] = (t & tmask[q]) | (w[q] & ~tmask[q]);
                     }
                 }
-                if (c_left > 0) issue(dep);
+                while (can_issue()) issue(dep);
             };
             auto store_rgba = [&](uint8_t *dst, uint32_t v) {
                 st_stream_v4(reinterpret_cast<uint4 *>(dst), make_uint4(s_rgba[v & 0xffu], s_rgba[(v >> 8) & 0xffu], s_rgba[(v >> 16) & 0xffu], s_rgba[v >> 24]));
@@ -608,66 +701,6 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                         else st_stream_u32(reinterpret_cast<uint32_t *>(dst), v);
                     }
                     o += p.out_stride;
-                }
-            }
-        } else if (A.tile < p.nbox + p.ngather) {
-            // ---- GATHER: lane = column, 32 rows; entries are read here (no prefetch: 32 registers)
-            const uint32_t *ent32 = reinterpret_cast<const uint32_t *>(p.entries + static_cast<size_t>(p.nbox) * kBoxBlockBytes +
-                                                                       static_cast<size_t>(A.tile - p.nbox) * kGatherBlockBytes);
-            uint32_t e[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) e[r] = __ldg(ent32 + r * kTileW + lane);
-            const uint32_t x = tile_x + lane;
-            if (x < width) {
-                uint32_t rows = min(32u, height - tile_y);
-                // unmapped pixels take the background once per unit
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    if (!(e[r] & BLINKY_LM_VALID)) {
-                        uint32_t bgv = 0;
-                        if (static_cast<uint32_t>(r) < rows) bgv = __ldg(p.bg + static_cast<size_t>(tile_y + r) * width + x);
-                        e[r] = bgv;  // valid bit clear, low byte = background value
-                    }
-                }
-                // software pipeline over the frames: the 32 byte gathers of frame f+1 are in flight while
-                // frame f is written (these tiles are bound by global-load latency, not by bytes)
-                auto gather_frame = [&](uint32_t frame, uint32_t (&v)[32]) {
-                    const uint8_t *__restrict__ faces = p.faces + static_cast<size_t>(frame) * p.face_stride;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        v[r] = e[r] & 0xffu;
-                        if (e[r] & BLINKY_LM_VALID) v[r] = ld_face(faces + (e[r] & BLINKY_LM_INDEX_MASK));
-                    }
-                };
-                auto store_frame = [&](uint32_t frame, const uint32_t (&v)[32]) {
-                    uint8_t *out_frame = static_cast<uint8_t *>(p.out) + static_cast<size_t>(frame) * p.out_stride;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        if (static_cast<uint32_t>(r) >= rows) break;
-                        uint32_t bv = v[r];
-                        if (RUBIX && (e[r] & BLINKY_LM_VALID)) {
-                            const uint32_t t = (e[r] >> BLINKY_LM_TINT_SHIFT) & 7u;
-                            if (t != BLINKY_LM_TINT_NONE) bv = s_lut[t * 256 + bv];
-                        }
-                        const size_t pix = static_cast<size_t>(tile_y + r) * width + x;
-                        if (RGBA) reinterpret_cast<uint32_t *>(out_frame)[pix] = s_rgba[bv];
-                        else out_frame[pix] = static_cast<uint8_t>(bv);
-                    }
-                };
-                // two value sets in turn (every read of a set follows its write in the same block: a set read
-                // before it is written in an iteration would be live around the whole unit loop)
-                uint32_t v0[32];
-                gather_frame(A.f0, v0);
-                for (uint32_t f = 0; f < A.nf; f += 2) {
-                    if (f + 1 < A.nf) {
-                        uint32_t v1[32];
-                        gather_frame(A.f0 + f + 1, v1);
-                        store_frame(A.f0 + f, v0);
-                        if (f + 2 < A.nf) gather_frame(A.f0 + f + 2, v0);
-                        store_frame(A.f0 + f + 1, v1);
-                    } else {
-                        store_frame(A.f0 + f, v0);
-                    }
                 }
             }
         } else {
@@ -867,13 +900,15 @@ WarpDevice::WarpDevice(int device) : device_(device) {
         throw std::runtime_error(buf);
     }
     sm_count_ = prop.multiProcessorCount;
+    smem_per_sm_ = prop.sharedMemPerMultiprocessor;
     if (const char *e = getenv("BLINKY_E2E_UPLOAD")) upload_by_kernel_ = strcmp(e, "kernel") == 0;
     if (const char *e = getenv("BLINKY_E2E_OUT")) out_by_kernel_ = strcmp(e, "direct") == 0;
     if (const char *e = getenv("BLINKY_E2E_BATCH")) batch_copies_ = atoi(e) != 0;
-    if (const char *e = getenv("BLINKY_RING_STAGES")) ring_stages_ = atoi(e);
+    if (const char *e = getenv("BLINKY_RING_BYTES")) ring_bytes_override_ = atoi(e);
+    if (const char *e = getenv("BLINKY_RING_BOXES")) ring_boxes_ = atoi(e);
     if (const char *e = getenv("BLINKY_RING_CTAS")) ring_ctas_cap_ = atoi(e);
     if (const char *e = getenv("BLINKY_FCHUNK")) fchunk_ = atoi(e);
-    if (const char *e = getenv("BLINKY_SPLIT_PERCENT")) split_percent_ = atoi(e);
+    if (const char *e = getenv("BLINKY_SERIAL_GATHER")) serial_gather_ = atoi(e) != 0;  // GATHER tiles in their own kernel before the ring kernel (A/B)
     if (const char *e = getenv("BLINKY_STATIC_PCT")) static_pct_ = std::max(0, std::min(100, atoi(e)));
     if (const char *e = getenv("BLINKY_L2_PROMOTION")) l2_promotion_ = atoi(e) & 3;  // 0 none, 1 64 B, 2 128 B, 3 256 B
     cudaStream_t s;
@@ -1088,15 +1123,25 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
     return t;
 }
 
-// kRingWarps = warps (one-warp CTAs) per SM the ring kernel's register allocation is sized for: 65536 / (32 x 12)
-// = 170 registers per thread.  (14 and 16 warps per SM with 144 / 128 registers were measured: slower, spills.)
-constexpr int kRingWarps = 12;
+// Warps (one-warp CTAs) per SM the ring kernel's register allocation is sized for: 20 (102 registers per thread; the
+// BOX path needs 100), 16 with the rubix overlay (128; needs 118).  How many actually fit is decided by shared
+// memory: the staging ring takes what an SM's shared memory leaves per warp (launch_ring).
+template <bool RUBIX>
+constexpr int ring_warps() { return 16; }
+// Resident ring warps per SM by default (BLINKY_RING_CTAS): measured on the 4K panini batch 12 / 14 / 16 warps give
+// 4.39 / 4.4 / 4.50 us per frame alone and 4.75 / 4.87 / 5.09 with the gather CTAs beside them — more warps only
+// spread the faces' L2 footprint; the registers left over go to the gather CTAs.
+constexpr int kRingWarpsDefault = 12;
+// GATHER tiles ride in the ring kernel's launch (gather_item) while they are at most this share of the plan; beyond
+// it (minifying lenses: thousands of GATHER tiles) the 256-thread gather kernel K3 in front of the ring kernel is
+// faster than tens of thousands of one-warp CTAs (measured: quincuncial 6.8 % -> 7.9 us serial vs 9.7 us merged).
+constexpr uint32_t kMergedGatherPercent = 5;
 
 template <bool RUBIX, bool RGBA>
 static cudaError_t ring_config(size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA, kRingWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(warp_ring_kernel<RUBIX, RGBA, ring_warps<RUBIX>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA, kRingWarps>, 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, warp_ring_kernel<RUBIX, RGBA, ring_warps<RUBIX>()>, 32, smem);
 }
 
 static cudaError_t ring_config_v(bool rubix, bool rgba, size_t smem, int *n) {
@@ -1107,10 +1152,10 @@ static cudaError_t ring_config_v(bool rubix, bool rgba, size_t smem, int *n) {
 }
 
 static void ring_launch_v(bool rubix, bool rgba, uint32_t grid, size_t smem, cudaStream_t st, const RingParams &p, const RingTmaps &tm) {
-    if (rubix && rgba) warp_ring_kernel<true, true, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
-    else if (rubix) warp_ring_kernel<true, false, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
-    else if (rgba) warp_ring_kernel<false, true, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
-    else warp_ring_kernel<false, false, kRingWarps><<<grid, 32, smem, st>>>(p, tm);
+    if (rubix && rgba) warp_ring_kernel<true, true, ring_warps<true>()><<<grid, 32, smem, st>>>(p, tm);
+    else if (rubix) warp_ring_kernel<true, false, ring_warps<true>()><<<grid, 32, smem, st>>>(p, tm);
+    else if (rgba) warp_ring_kernel<false, true, ring_warps<false>()><<<grid, 32, smem, st>>>(p, tm);
+    else warp_ring_kernel<false, false, ring_warps<false>()><<<grid, 32, smem, st>>>(p, tm);
 }
 
 bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_out, size_t out_stride, int nframes,
@@ -1142,20 +1187,41 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     p.zero = 0;
     p.lab = 0;
     if (const char *e = getenv("BLINKY_LAB")) p.lab = static_cast<uint32_t>(atoi(e));
+    p.lab_bytes = shapes_.empty() ? 128u : static_cast<uint32_t>((shapes_[0] >> 8) * (shapes_[0] & 0xff) * 128);
     const bool rubix = rubix_;
     const int vi = (rubix ? 1 : 0) | (rgba ? 2 : 0);
-    // Tiles [0, nbox) are BOX tiles.  A few GATHER/EMPTY tiles ride along in the ring kernel (one launch,
-    // one warp each, frames software-pipelined); when they are many (strong minification, large unmapped
-    // borders) they go to the gather kernel K3, which hides their load latency with plain parallelism.
-    const bool split = (ntiles_ - nbox_tiles_) * 100u > ntiles_ * static_cast<uint32_t>(split_percent_);
-    const uint32_t ring_tiles = split ? nbox_tiles_ : ntiles_;
-    // ring geometry: stages hold the plan's largest box
-    p.stage_bytes = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
-    // two stages per warp keep a multi-frame unit fed; single-frame launches (the in-engine shape) consume a
-    // stage per unit and want one more box in flight
-    p.nstages = ring_stages_ > 0 ? static_cast<uint32_t>(ring_stages_) : (p.stage_bytes <= 4096 || (nframes == 1 && p.stage_bytes <= 8192) ? 3u : 2u);
-    if (p.nstages > static_cast<uint32_t>(kRingMaxStages)) p.nstages = kRingMaxStages;
-    const size_t smem = static_cast<size_t>(p.stage_bytes) * p.nstages + kRingBarBytes + kBoxBlockBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
+    // The ring kernel takes the BOX tiles [0, nbox) and the EMPTY tiles; the GATHER tiles in between go to the
+    // gather kernel K3 on the context's side stream (forked from and joined to the caller's stream), so the two
+    // kernels share the GPU instead of queueing behind each other.
+    const uint32_t nempty = ntiles_ - nbox_tiles_ - ngather_tiles_;
+    const uint32_t ring_tiles = nbox_tiles_ + nempty;
+    // Ring geometry: as many warps per SM as the registers allow (or BLINKY_RING_CTAS), each with the largest
+    // staging ring that still lets that many CTAs share the SM's shared memory; fewer warps if the plan's
+    // largest box would not fit such a ring.
+    const size_t fixed = kRingBarBytes + kBoxBlockBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
+    const uint32_t max_box = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
+    const bool merged_gather = !serial_gather_ && ngather_tiles_ > 0 && ngather_tiles_ * 100u <= ntiles_ * kMergedGatherPercent;
+    int want = std::min(kRingWarpsDefault, rubix ? ring_warps<true>() : ring_warps<false>());
+    if (ring_ctas_cap_ > 0) want = std::min(ring_ctas_cap_, rubix ? ring_warps<true>() : ring_warps<false>());
+    // ring size: twice the plan's largest box (two boxes of any size in flight; measured on the 4K panini plan, largest
+    // box 6.4 KB: 8 KB ring 5.2 us per frame, 12 KB 4.7), as far as `want` resident warps — plus two gather CTAs, which
+    // carry the same allocation, when GATHER tiles ride along — leave room in the SM's shared memory
+    uint32_t ring_bytes = 0;
+    for (; want >= 1; --want) {
+        const size_t per_cta = smem_per_sm_ / static_cast<size_t>(want + (merged_gather ? 2 : 0));
+        if (per_cta < 1024 + fixed + max_box) continue;
+        const uint32_t room = static_cast<uint32_t>((per_cta - 1024 - fixed) / 128 * 128);
+        ring_bytes = std::min(room, std::max(2u * max_box, 8192u));
+        if (ring_bytes_override_ > 0) ring_bytes = std::min(room, std::max<uint32_t>(max_box, static_cast<uint32_t>(ring_bytes_override_) / 128 * 128));
+        break;
+    }
+    if (want < 1) {
+        err_ = "ring kernel: the plan's largest box does not fit the staging ring";
+        return false;
+    }
+    p.ring_bytes = ring_bytes;
+    p.max_inflight = static_cast<uint32_t>(std::max(1, std::min(ring_boxes_, kRingBoxes)));
+    const size_t smem = static_cast<size_t>(ring_bytes) + fixed;
     if (ring_ctas_per_sm_[vi] == 0 || ring_smem_[vi] != smem) {
         int n = 0;
         cudaError_t e = ring_config_v(rubix, rgba, smem, &n);
@@ -1167,8 +1233,7 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
         ring_ctas_per_sm_[vi] = n;
         ring_smem_[vi] = smem;
     }
-    int ctas = ring_ctas_per_sm_[vi];
-    if (ring_ctas_cap_ > 0 && ctas > ring_ctas_cap_) ctas = ring_ctas_cap_;
+    int ctas = std::min(ring_ctas_per_sm_[vi], want);
     uint32_t grid = static_cast<uint32_t>(sm_count_ * ctas);
     // frames per unit: a unit pays a fixed cost (entry unpack, ring refill across the boundary: ~0.8 frame
     // times) and the launch ends with a tail of about one unit; pick the chunk that minimises
@@ -1187,8 +1252,25 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     p.nchunks = (p.nframes + fchunk - 1) / fchunk;
     p.nunits = ring_tiles * p.nchunks;
     if (grid > p.nunits) grid = p.nunits;
-    char buf[512];
+    char buf[640];
     int nbuf = 0;
+    // GATHER tiles: one-warp CTAs behind the ring warps in the same grid (see gather_item); only a plan without BOX and
+    // EMPTY tiles launches the stand-alone gather kernel.
+    uint32_t ngather = ngather_tiles_;
+#ifdef BLINKY_LAB
+    if (getenv("BLINKY_LAB_NOK3")) ngather = 0;  // time the ring warps alone
+#endif
+    const uint32_t gather_items = ngather * (kTileH / kGatherRows) * static_cast<uint32_t>((nframes + kGatherFrames - 1) / kGatherFrames);
+    buf[0] = 0;
+    if (ngather > 0 && (grid == 0 || !merged_gather)) {
+        dim3 g2(ngather, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
+        if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, nbox_tiles_);
+        else if (rubix) warp_tile_gather_kernel<true, false><<<g2, kThreads, 0, st>>>(p, nbox_tiles_);
+        else if (rgba) warp_tile_gather_kernel<false, true><<<g2, kThreads, 0, st>>>(p, nbox_tiles_);
+        else warp_tile_gather_kernel<false, false><<<g2, kThreads, 0, st>>>(p, nbox_tiles_);
+        ++launches_;
+        snprintf(buf, sizeof buf, "warp_tile_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", rubix, rgba, g2.x, g2.y, kThreads);
+    }
     if (grid > 0) {
         // ticket counter of this stream (launches on one stream are serialised; the counter is never reset:
         // the kernel subtracts the value it had when the launch started)
@@ -1226,24 +1308,15 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
         }
         tc->base += good + drawers;
 
-        ring_launch_v(rubix, rgba, grid, smem, st, p, *tm);
+        p.ring_grid = grid;
+        const uint32_t extra = merged_gather ? gather_items : 0u;
+        ring_launch_v(rubix, rgba, grid + extra, smem, st, p, *tm);
         ++launches_;
-        nbuf = snprintf(buf, sizeof buf, "warp_ring_kernel<rubix=%d,rgba=%d> grid=%u block=32 (%d warps/SM, %u-stage TMA ring of %u B, %u frames/unit, %u units)", rubix,
-                        rgba, grid, ctas, p.nstages, p.stage_bytes, fchunk, p.nunits);
-    }
-    uint32_t nother = ntiles_ - ring_tiles;
-#ifdef BLINKY_LAB
-    if (getenv("BLINKY_LAB_NOK3")) nother = 0;  // time the ring kernel alone
-#endif
-    if (nother > 0) {
-        dim3 g2(nother, static_cast<unsigned>((nframes + kGatherFramesPerCta - 1) / kGatherFramesPerCta));
-        if (rubix && rgba) warp_tile_gather_kernel<true, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else if (rubix) warp_tile_gather_kernel<true, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else if (rgba) warp_tile_gather_kernel<false, true><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        else warp_tile_gather_kernel<false, false><<<g2, kThreads, 0, st>>>(p, ring_tiles);
-        ++launches_;
-        snprintf(buf + nbuf, sizeof buf - static_cast<size_t>(nbuf), "%swarp_tile_gather_kernel<rubix=%d,rgba=%d> grid=(%u,%u) block=%d", nbuf ? " + " : "", rubix,
-                 rgba, g2.x, g2.y, kThreads);
+        nbuf = static_cast<int>(strlen(buf));
+        snprintf(buf + nbuf, sizeof buf - static_cast<size_t>(nbuf),
+                 "%swarp_ring_kernel<rubix=%d,rgba=%d> grid=%u+%u block=32 (%d ring warps/SM, TMA box ring of %u B, <=%u boxes in flight, %u frames/unit, %u units; "
+                 "%u gather CTAs of %dx32 px x %d frames)",
+                 nbuf ? " + " : "", rubix, rgba, grid, extra, ctas, p.ring_bytes, p.max_inflight, fchunk, p.nunits, extra, kGatherRows, kGatherFrames);
     }
     last_kernel_ = buf;
     CK(cudaGetLastError());

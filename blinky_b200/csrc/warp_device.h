@@ -108,8 +108,10 @@ private:
     int stage_bytes_ = 0;                // largest staged box of the plan
     int static_pct_ = 85;                // share of the ring kernel's units scheduled statically (BLINKY_STATIC_PCT)
     int l2_promotion_ = 0;               // CUtensorMapL2promotion of the box descriptors (BLINKY_L2_PROMOTION)
-    int split_percent_ = 12;             // GATHER+EMPTY share of tiles above which they get their own kernel (BLINKY_SPLIT_PERCENT)
-    int ring_stages_ = 0, ring_ctas_cap_ = 0, fchunk_ = 0;  // tuning overrides (BLINKY_RING_STAGES / _CTAS, BLINKY_FCHUNK); 0 = automatic
+    bool serial_gather_ = false;         // BLINKY_SERIAL_GATHER=1: GATHER tiles in their own kernel instead of as extra CTAs of the ring kernel's launch
+    int ring_bytes_override_ = 0, ring_ctas_cap_ = 0, fchunk_ = 0;  // tuning overrides (BLINKY_RING_BYTES / _CTAS, BLINKY_FCHUNK); 0 = automatic
+    int ring_boxes_ = 2;                 // boxes a warp keeps in flight at most (BLINKY_RING_BOXES)
+    size_t smem_per_sm_ = 233472;
     std::vector<uint16_t> shapes_;
     std::vector<TmapSet *> tmap_sets_;   // small cache keyed by (faces ptr, stride, nframes)
     uint64_t tmap_tick_ = 0;
