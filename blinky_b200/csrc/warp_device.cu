@@ -166,26 +166,32 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 
 
 // --------------------------------------------------------------------------
-// K2: ring kernel.  Every WARP is its own pipeline (one warp per CTA, as many CTAs per SM as
-// shared memory allows): it draws work units (tile, chunk of frames) from a ticket counter,
-// keeps the tile's lensmap entries in REGISTERS for all frames of the unit, and feeds itself
-// through a private ring of TMA tensor loads:
-//   * per unit: 4 coalesced 128-bit loads give the lane its 32 16-bit entries (prefetched one
-//     unit ahead); they are unpacked once into 32 shared-memory offsets.
+// K2: ring kernel.  Every WARP is its own pipeline (one warp per CTA, 12 resident per SM): it
+// takes work units (tile, chunk of frames) — most from a static schedule, the tail from a ticket
+// counter —, keeps the tile's lensmap entries in REGISTERS for all frames of the unit, and feeds
+// itself through a private ring of TMA tensor loads:
+//   * per unit: the tile's entry block (2 KB of 16-bit offsets) arrives by a bulk copy
+//     (cp.async.bulk) into the warp's entry buffer, issued a whole unit ahead; the lane reads its
+//     32 entries from there with four 128-bit shared loads and unpacks them once.
 //   * per frame: lane 0 has issued ONE 4-D TMA tensor load (x, y, plate, frame) of the tile's
-//     source box into a ring stage, completing on the stage's mbarrier; the warp waits, does
-//     32 byte loads from shared memory per lane (one per output pixel), packs them with PRMT
-//     into eight 32-bit words and writes them with streaming stores; the stage is refilled with
-//     the next box of the warp's sequence (this unit's later frames, then the next unit's first
-//     frames) as soon as its data sits in registers.
-// There is no producer warp, no cross-warp barrier and no per-pixel entry traffic per frame:
-// round 1's kernel was bound by the serial per-item work of its producer thread (5.2 us/frame
-// with every load and store removed, profiles/r2_c1_k2lab.txt).
+//     source box into the warp's byte ring, completing on an mbarrier; the warp waits, does 32
+//     byte loads from shared memory per lane (one per output pixel), packs them with PRMT into
+//     eight 32-bit words and writes them with streaming stores; the next box of the warp's
+//     sequence (this unit's later frames, then the next units' first frames) is issued as soon as
+//     the consumed box's bytes sit in registers.
+// There is no producer warp, no cross-warp barrier, no per-pixel entry traffic per frame, and no
+// global load on a scoreboard in the frame loop.  History, all measured (profiles/r2_c1*_sweep.jsonl):
+// round 1's kernel was bound by the serial per-item work of its producer thread; the first
+// self-feeding version spent 36 of 213 instructions per frame copying registers that an
+// uninitialised array in the GATHER path kept live around the unit loop, and the GATHER path's 130
+// registers capped the kernel at 160 registers per thread.  Now the frame loop is ~140
+// instructions at 96 registers.  What is left is not one bottleneck: with the 4K panini batch at
+// 4.4 us per frame (ring warps alone), removing the stores gives 3.2, removing the box loads 3.4,
+// both 2.6, conflict-free shared loads 4.4, 128-byte instead of 32-byte store segments 4.3 — DRAM
+// time (2.7 us for the 17.5 MB a frame moves) and issue time overlap only partly with 12 warps,
+// and more warps or deeper rings lose as much L2 locality as they gain latency hiding.
 // EMPTY tiles copy the background.  GATHER tiles (plate seams, singular points, boxes too large to
-// stage) are not this kernel's: their direct global gathers need ~130 registers per thread for the
-// loads in flight, which capped the whole kernel at 12 warps per SM while the BOX path needs 100
-// (measured: time = 2.8 us + 19.8 us / warps-per-SM per 4K frame).  They go to the gather kernel K3,
-// launched on a second stream so that it runs beside this kernel.
+// stage) are not the ring warps': see gather_item.
 // --------------------------------------------------------------------------
 constexpr int kRingBoxes = 6;                                 // boxes in flight per warp at most (one mbarrier each)
 constexpr int kRingBarBytes = (kRingBoxes + 1) * 8 + 8;       // mbarriers (+ the entry buffer's), padded to 16 bytes
@@ -260,11 +266,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -319,6 +320,22 @@ __device__ __forceinline__ void st_stream_u32x8(const uint64_t (&a)[8], const ui
           "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
         : "memory");
 }
+
+#ifdef BLINKY_LAB
+#define LAB_ST8(POL)                                                                                                        \
+    asm volatile("st.global" POL ".u32 [%0], %8;\n\tst.global" POL ".u32 [%1], %9;\n\tst.global" POL ".u32 [%2], %10;\n\t"    \
+                 "st.global" POL ".u32 [%3], %11;\n\tst.global" POL ".u32 [%4], %12;\n\tst.global" POL ".u32 [%5], %13;\n\t"  \
+                 "st.global" POL ".u32 [%6], %14;\n\tst.global" POL ".u32 [%7], %15;"                                        \
+                 ::"l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7]), "r"(w[0]), "r"(w[1]), \
+                   "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory")
+// store cache policy experiment: 0 .cs (shipped), 1 default (.wb), 2 .cg, 3 .wt
+__device__ __forceinline__ void st_lab_u32x8(const uint64_t (&a)[8], const uint32_t (&w)[8], uint32_t pol) {
+    if (pol == 1) LAB_ST8("");
+    else if (pol == 2) LAB_ST8(".cg");
+    else if (pol == 3) LAB_ST8(".wt");
+    else LAB_ST8(".cs");
+}
+#endif
 
 // ---- gather role of the ring kernel's launch ---------------------------------------------------------------
 // GATHER tiles (plate seams, singular points, boxes too large to stage) read the globe directly: 32-bit
@@ -376,7 +393,7 @@ __device__ __forceinline__ void gather_item(const RingParams &p, uint32_t item, 
     }
 }
 
-// MINB: warps (= CTAs) per SM the register allocation is sized for
+// MINB: CTAs per SM the register allocation is sized for (ring warps plus the gather CTAs beside them)
 template <bool RUBIX, bool RGBA, int MINB>
 __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_constant__ RingParams p, const __grid_constant__ RingTmaps tm) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -662,7 +679,8 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
 #pragma unroll
                             for (int q = 0; q < 8; ++q) a[q] = reinterpret_cast<uint64_t>(fb + q * 128 + lane * 4u);
                         }
-                        if (!(p.lab & 1u) || w[0] == 0x12345679u)
+                        if ((p.lab >> 8) & 3u) st_lab_u32x8(a, w, (p.lab >> 8) & 3u);
+                        else if (!(p.lab & 1u) || w[0] == 0x12345679u)
 #endif
                         st_stream_u32x8(a, w);
                     }
@@ -736,10 +754,11 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
 }
 
 // --------------------------------------------------------------------------
-// K3: companion of the ring kernel for plans in which many tiles cannot be staged (GATHER: plate
-// seams, singular points, minification too strong for a 16 KB box; EMPTY: background only).  Those
-// tiles are bound by global-load latency, which one warp per tile hides badly; here they get plain
-// parallelism: grid = (tiles, groups of 4 frames), 256 threads, a warp owns 4 tile rows and lane l is
+// K3: the GATHER tiles of plans in which they are many (more than kMergedGatherPercent of the tiles:
+// minifying lenses, where a tile's texels do not fit a box), launched in front of the ring kernel; with
+// few GATHER tiles they ride in the ring kernel's launch instead (gather_item).  Those tiles are bound
+// by global-load latency and, at 32-byte sectors scattered over DRAM pages, by DRAM itself (ncu: 47 %
+// of DRAM peak with one useful byte in 18 fetched); they get plain parallelism: grid = (tiles, groups of 4 frames), 256 threads, a warp owns 4 tile rows and lane l is
 // column l (one warp-level load = 32 consecutive screen pixels of one row).  The tile's entries are
 // fetched once and reused for the frames of the group; all 16 gathers of a thread are issued before
 // its first store.
@@ -1123,9 +1142,8 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
     return t;
 }
 
-// Warps (one-warp CTAs) per SM the ring kernel's register allocation is sized for: 20 (102 registers per thread; the
-// BOX path needs 100), 16 with the rubix overlay (128; needs 118).  How many actually fit is decided by shared
-// memory: the staging ring takes what an SM's shared memory leaves per warp (launch_ring).
+// CTAs per SM the ring kernel's register allocation is sized for: 16 (128 registers per thread; the BOX path uses 96,
+// 118 with the rubix overlay).  How many ring warps are resident is decided in launch_ring.
 template <bool RUBIX>
 constexpr int ring_warps() { return 16; }
 // Resident ring warps per SM by default (BLINKY_RING_CTAS): measured on the 4K panini batch 12 / 14 / 16 warps give
