@@ -1492,23 +1492,28 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
                 for (size_t y = 0; y < rh; ++y) memcpy(s.h_faces + off + y * platesize_, from + y * platesize_, rw);
                 from = s.h_faces + off;
             }
+            // a full-width rectangle is one contiguous run: copy it as such (the DMA engines move long runs faster than
+            // pitched rows)
+            const bool contiguous = rw == static_cast<size_t>(platesize_);
             if (batch_copies_) {  // all rectangles of the frame in ONE driver call (no gap between six DMA operations)
                 cudaMemcpy3DBatchOp &op = ops[nops++];
                 memset(&op, 0, sizeof op);
+                const size_t row = contiguous ? rw * rh : static_cast<size_t>(platesize_), rows = contiguous ? 1 : rh;
                 op.src.type = cudaMemcpyOperandTypePointer;
                 op.src.op.ptr.ptr = const_cast<uint8_t *>(from);
-                op.src.op.ptr.rowLength = static_cast<size_t>(platesize_);
-                op.src.op.ptr.layerHeight = rh;
+                op.src.op.ptr.rowLength = row;
+                op.src.op.ptr.layerHeight = rows;
                 op.dst.type = cudaMemcpyOperandTypePointer;
                 op.dst.op.ptr.ptr = s.d_faces + off;
-                op.dst.op.ptr.rowLength = static_cast<size_t>(platesize_);
-                op.dst.op.ptr.layerHeight = rh;
-                op.extent = make_cudaExtent(rw, rh, 1);
+                op.dst.op.ptr.rowLength = row;
+                op.dst.op.ptr.layerHeight = rows;
+                op.extent = make_cudaExtent(contiguous ? rw * rh : rw, rows, 1);
                 op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
                 continue;
             }
-            cudaError_t e = cudaMemcpy2DAsync(s.d_faces + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
-                                              cudaMemcpyHostToDevice, s.stream);
+            cudaError_t e = contiguous ? cudaMemcpyAsync(s.d_faces + off, from, rw * rh, cudaMemcpyHostToDevice, s.stream)
+                                       : cudaMemcpy2DAsync(s.d_faces + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
+                                                           cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
         }
         if (ok && nops > 0) {
@@ -1519,7 +1524,7 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
                 cudaGetLastError();
                 batch_copies_ = false;
                 for (size_t k = 0; k < nops && ok; ++k) {
-                    e = cudaMemcpy2DAsync(ops[k].dst.op.ptr.ptr, static_cast<size_t>(platesize_), ops[k].src.op.ptr.ptr, static_cast<size_t>(platesize_),
+                    e = cudaMemcpy2DAsync(ops[k].dst.op.ptr.ptr, ops[k].dst.op.ptr.rowLength, ops[k].src.op.ptr.ptr, ops[k].src.op.ptr.rowLength,
                                           ops[k].extent.width, ops[k].extent.height, cudaMemcpyHostToDevice, s.stream);
                     if (e != cudaSuccess) ok = fail("cudaMemcpy2DAsync(H2D faces)", e);
                 }
@@ -1546,6 +1551,8 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
         cudaError_t e;
         if (zero_copy_out) {
             e = cudaSuccess;
+        } else if (s.direct && dst_rowbytes == W) {   // a tightly packed destination: one contiguous run
+            e = cudaMemcpyAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, s.d_out, static_cast<size_t>(W) * H, cudaMemcpyDeviceToHost, s.stream);
         } else if (s.direct) {
             e = cudaMemcpy2DAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, static_cast<size_t>(dst_rowbytes), s.d_out,
                                   static_cast<size_t>(W), static_cast<size_t>(W), static_cast<size_t>(H), cudaMemcpyDeviceToHost, s.stream);
