@@ -925,6 +925,7 @@ WarpDevice::WarpDevice(int device) : device_(device) {
     if (const char *e = getenv("BLINKY_E2E_BATCH")) batch_copies_ = atoi(e) != 0;
     if (const char *e = getenv("BLINKY_RING_BYTES")) ring_bytes_override_ = atoi(e);
     if (const char *e = getenv("BLINKY_RING_BOXES")) ring_boxes_ = atoi(e);
+    if (const char *e = getenv("BLINKY_MERGED_ITEMS")) merged_items_max_ = atoi(e);
     if (const char *e = getenv("BLINKY_RING_CTAS")) ring_ctas_cap_ = atoi(e);
     if (const char *e = getenv("BLINKY_FCHUNK")) fchunk_ = atoi(e);
     if (const char *e = getenv("BLINKY_SERIAL_GATHER")) serial_gather_ = atoi(e) != 0;  // GATHER tiles in their own kernel before the ring kernel (A/B)
@@ -1218,7 +1219,10 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     // largest box would not fit such a ring.
     const size_t fixed = kRingBarBytes + kBoxBlockBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
     const uint32_t max_box = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
-    const bool merged_gather = !serial_gather_ && ngather_tiles_ > 0 && ngather_tiles_ * 100u <= ntiles_ * kMergedGatherPercent;
+    // (few gather items in absolute terms — short launches — also ride along: a second kernel launch costs more than they do)
+    const uint32_t all_gather_items = ngather_tiles_ * (kTileH / kGatherRows) * static_cast<uint32_t>((nframes + kGatherFrames - 1) / kGatherFrames);
+    const bool merged_gather = !serial_gather_ && ngather_tiles_ > 0 &&
+                               (ngather_tiles_ * 100u <= ntiles_ * kMergedGatherPercent || all_gather_items <= static_cast<uint32_t>(merged_items_max_));
     int want = std::min(kRingWarpsDefault, rubix ? ring_warps<true>() : ring_warps<false>());
     if (ring_ctas_cap_ > 0) want = std::min(ring_ctas_cap_, rubix ? ring_warps<true>() : ring_warps<false>());
     // ring size: twice the plan's largest box (two boxes of any size in flight; measured on the 4K panini plan, largest

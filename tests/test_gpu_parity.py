@@ -56,6 +56,44 @@ def test_native_library_is_what_runs(bb, fe):
     assert bb.LIB_PATH in maps
 
 
+RING_KNOBS = [
+    {},                                                      # shipped defaults
+    {"BLINKY_SERIAL_GATHER": "1"},                           # GATHER tiles in K3 instead of as CTAs of the ring kernel's launch
+    {"BLINKY_MERGED_ITEMS": "1000000"},                      # ... and the other way round: always in the ring kernel's launch
+    {"BLINKY_RING_CTAS": "2", "BLINKY_STATIC_PCT": "0"},     # few warps, every unit from the ticket counter: long unit sequences per warp
+    {"BLINKY_RING_CTAS": "16", "BLINKY_STATIC_PCT": "100"},  # as many warps as the registers allow, no tickets
+    {"BLINKY_RING_BYTES": "128", "BLINKY_RING_BOXES": "6"},  # the smallest ring the plan allows (its largest box): wraps all the time
+    {"BLINKY_RING_BYTES": "32768", "BLINKY_RING_BOXES": "6", "BLINKY_RING_CTAS": "4"},  # a deep ring: six boxes of a warp in flight
+    {"BLINKY_FCHUNK": "1"}, {"BLINKY_FCHUNK": "3"}, {"BLINKY_FCHUNK": "16"},             # unit = 1 / 3 / all frames
+]
+
+
+@pytest.mark.parametrize("knobs", RING_KNOBS, ids=lambda k: ",".join(f"{a[7:]}={b}" for a, b in k.items()) or "default")
+def test_ring_kernel_schedules_and_ring_geometries(bb, restate, palette, torch_mod, cuda_device, knobs, monkeypatch):
+    """The ring kernel's tuning knobs change how units are handed out, how many boxes a warp keeps in flight and
+    where they sit in its byte ring — never the pixels.  Two plans: one with BOX, GATHER and EMPTY tiles and the
+    rubix overlay (hammer on a tetrahedron), one with large boxes (quincuncial), five frames each, against the oracle."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    pm = restate.palmaps(palette)
+    for globe, lens, zoom, (W, H, PS), rubix in (("tetra", "hammer", "f_contain", (1000, 562, 512), True),
+                                                 ("cube", "quincuncial", "f_cover", (1280, 720, 1024), False)):
+        with bb.Fisheye(device=cuda_device, palette=palette) as f:   # the knobs are read when the context is created
+            setup(f, globe, lens, W, H, PS, zoom, rubix)
+            bg = bb.synthetic_background(W, H)
+            f.set_background(bg)
+            idx, tint = f.lensmap()
+            nf = 5
+            faces = np.stack([bb.synthetic_faces(f.numplates, PS, 40 + i) for i in range(nf)])
+            got = gpu_warp(torch_mod, f, faces, nframes=nf)
+            assert "warp_ring_kernel" in f.last_kernel
+            for i in range(nf):
+                want = restate.render(idx, tint, faces[i], pm, rubix, background=bg)
+                assert np.array_equal(got[i], want), (knobs, lens, i, f.last_kernel)
+            one = gpu_warp(torch_mod, f, faces[3:4], nframes=1)[0]
+            assert np.array_equal(one, got[3]), (knobs, lens, "single frame", f.last_kernel)
+
+
 @pytest.mark.parametrize("rubix", [False, True])
 @pytest.mark.parametrize("kernel", [0, 1])
 def test_c1_against_oracle_and_golden(bb, fe, restate, palette, torch_mod, rubix, kernel):
