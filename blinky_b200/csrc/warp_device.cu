@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // EMPTY tiles copy the background.  GATHER tiles (plate seams, singular points, boxes too large to
 // stage) are not the ring warps': see gather_item.
 // --------------------------------------------------------------------------
-constexpr int kRingBoxes = 6;                                 // boxes in flight per warp at most (one mbarrier each)
-constexpr int kRingBarBytes = (kRingBoxes + 1) * 8 + 8;       // mbarriers (+ the entry buffer's), padded to 16 bytes
-static_assert(kRingBarBytes % 16 == 0 && kBoxBlockBytes % 16 == 0, "the entry buffer is read with 128-bit loads");
+constexpr int kRingBoxes = 6;                                 // items (boxes, entry blocks) in flight per warp at most (one mbarrier each)
+constexpr int kRingBarBytes = kRingBoxes * 8 + 16;            // mbarriers, padded to a multiple of 16 bytes
+static_assert(kRingBarBytes % 16 == 0 && kBoxBlockBytes % 128 == 0, "ring items are multiples of 128 bytes (TMA destinations), entry blocks are read with 128-bit loads");
 
 struct RingParams {
     const TileDesc *tiles;
@@ -407,14 +407,11 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     const uint32_t R = p.ring_bytes;
     const uint32_t ring = smem_u32(smem_raw);
     uint8_t *tail = smem_raw + static_cast<size_t>(R);
-    const uint32_t bars = smem_u32(tail);                             // kRingBoxes box barriers + the entry buffer's
-    const uint32_t ebar = bars + kRingBoxes * 8;
-    const uint32_t ebuf = smem_u32(tail + kRingBarBytes);             // entry block of the next BOX unit (kBoxBlockBytes)
-    uint8_t *s_lut = tail + kRingBarBytes + kBoxBlockBytes;           // [6][256] plate LUTs
+    const uint32_t bars = smem_u32(tail);                             // kRingBoxes barriers, one per item in flight
+    uint8_t *s_lut = tail + kRingBarBytes;                            // [6][256] plate LUTs
     uint32_t *s_rgba = reinterpret_cast<uint32_t *>(s_lut + (RUBIX ? 6 * 256 : 0));
     if (lane == 0) {
         for (uint32_t s = 0; s < kRingBoxes; ++s) mbar_init(bars + 8 * s, 1);
-        mbar_init(ebar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (RUBIX) {
@@ -448,19 +445,6 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
         return u;
     };
     auto is_box = [&](const RingUnit &u) { return u.ticket < p.nunits && u.tile < p.nbox; };
-    // Entry block of a BOX unit: fetched by a bulk copy into the warp's entry buffer a whole unit before it
-    // is needed, unpacked from there into registers when the unit starts (no registers are held for it in
-    // between, and the copy does not sit on a scoreboard).  e_ticket = the unit whose block is in the
-    // buffer or on its way.
-    uint32_t e_ticket = 0xffffffffu, e_phase = 0;
-    auto fetch_entries = [&](const RingUnit &u, uint32_t dep) {
-        if (lane == 0) {
-            mbar_expect_tx(ebar, kBoxBlockBytes);
-            bulk_load(ebuf + dep, p.entries + static_cast<size_t>(u.tile) * kBoxBlockBytes, kBoxBlockBytes, ebar);
-        }
-        e_ticket = u.ticket;
-    };
-
     // Work distribution: the first `nstatic` units of a warp are fixed (w, w + NW, ...), the rest of the
     // launch is handed out through the ticket counter.  Mostly static because one counter serves the
     // whole GPU and same-address atomics serialise; the dynamic tail evens out the finish.
@@ -484,12 +468,12 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
     RingUnit A = describe(draw_now());
     RingUnit B = describe(draw_now());
     RingUnit C = describe(draw_now());
-    if (is_box(A)) fetch_entries(A, 0);
 
-    // Ring state (warp-uniform).  The ring is a byte FIFO: a box goes behind the previous one, or at offset 0 when
-    // it would run over the end — a rule the consuming side repeats with the same box sizes, so no positions are
-    // passed along.  Small boxes therefore cost small space, and a warp with 2 KB boxes has four in flight where
-    // fixed stages sized for the plan's largest box held two.
+    // Ring state (warp-uniform).  The ring is a byte FIFO of ITEMS — per BOX unit its entry block (bulk copy) followed by
+    // one box per frame (TMA tensor load): an item goes behind the previous one, or at offset 0 when it would run over
+    // the end — a rule the consuming side repeats with the same sizes, so no positions are passed along.  Small boxes
+    // cost small space; the entry block of the next unit(s) is on its way while this unit's frames are warped, as deep
+    // as the cursor may run ahead (single-frame launches: entry blocks and boxes of two units on).
     //   ipos   where the next box goes        cpos   end of the last consumed box (everything in flight lies
     //   is/cs  barrier slot of the next box to issue / to consume, phases: their parity bits     behind it)
     uint32_t cs = 0, is = 0, phases = 0, inflight = 0, ipos = 0, cpos = 0;
@@ -498,11 +482,13 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
         if (ipos > cpos) return ipos + n <= R || n <= cpos; // in flight: [cpos, ipos)
         return ipos + n <= cpos;                            // in flight: [cpos, R) and [0, ipos)
     };
-    // Issue cursor: the next box of the warp's sequence — this unit's frames in order, then the frames of the
-    // next BOX units (single-frame launches, the in-engine shape, need the look-ahead to reach two units on).
-    // Its TMA operands are worked out when the cursor enters a unit, not per box.
+    // Issue cursor: the next item of the warp's sequence — this unit's entry block and frames in order, then those of
+    // the next BOX units (single-frame launches, the in-engine shape, need the look-ahead to reach two units on).
+    // Its TMA operands are worked out when the cursor enters a unit, not per item.
     //   c_unit   0/1/2 = A/B/C: the unit the cursor is in (c_left > 0) or will look at next (c_left == 0)
-    uint32_t c_unit = 0, c_left = 0, c_frame = 0, c_bytes = 0;
+    //   c_left   items of that unit still to issue (entry block + frames), c_entry: the next one is the entry block
+    uint32_t c_unit = 0, c_left = 0, c_frame = 0, c_bytes = 0, c_tile = 0;
+    bool c_entry = false;
     uint64_t c_tmap = 0;
     int c_bx = 0, c_by = 0, c_plate = 0;
     auto seat = [&]() {   // move the cursor to the first unit at or after c_unit that still has boxes to issue
@@ -513,7 +499,9 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
             if (ticket < p.nunits && tile < p.nbox) {
                 const uint32_t dy = c_unit == 0 ? A.dy : c_unit == 1 ? B.dy : C.dy;
                 const uint32_t dz = c_unit == 0 ? A.dz : c_unit == 1 ? B.dz : C.dz;
-                c_left = c_unit == 0 ? A.nf : c_unit == 1 ? B.nf : C.nf;
+                c_left = (c_unit == 0 ? A.nf : c_unit == 1 ? B.nf : C.nf) + 1u;
+                c_entry = true;
+                c_tile = tile;
                 c_frame = c_unit == 0 ? A.f0 : c_unit == 1 ? B.f0 : C.f0;
                 c_tmap = reinterpret_cast<uint64_t>(&tm.m[(dz >> (8 + kTileShapeShift)) & 63u]);
                 c_bx = static_cast<int16_t>(dy & 0xffffu);
@@ -531,27 +519,30 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
             }
         }
     };
-    auto can_issue = [&]() { return c_left > 0 && inflight < p.max_inflight && room_for(c_bytes); };
+    auto can_issue = [&]() { return c_left > 0 && inflight < p.max_inflight && room_for(c_entry ? static_cast<uint32_t>(kBoxBlockBytes) : c_bytes); };
     auto issue = [&](uint32_t dep) {   // precondition: can_issue()
+        const uint32_t n = c_entry ? static_cast<uint32_t>(kBoxBlockBytes) : c_bytes;
         if (inflight == 0) ipos = cpos = 0;   // (an empty ring restarts at the front: keeps "everything in flight lies behind cpos" true)
-        if (ipos + c_bytes > R) ipos = 0;
+        if (ipos + n > R) ipos = 0;
 #ifdef BLINKY_LAB
-        if (lane == 0 && !(p.lab & 16u)) {
-            const uint32_t bar = bars + 8 * is;
-            mbar_expect_tx(bar, c_bytes);
-            tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, (p.lab & 8u) ? 0 : static_cast<int>(c_frame), bar);
-        }
+        if (lane == 0 && (c_entry || !(p.lab & 16u))) {
 #else
         if (lane == 0) {
-            const uint32_t bar = bars + 8 * is;
-            mbar_expect_tx(bar, c_bytes);
-            tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, static_cast<int>(c_frame), bar);
-        }
 #endif
-        ipos += c_bytes;
+            const uint32_t bar = bars + 8 * is;
+            mbar_expect_tx(bar, n);
+            if (c_entry) bulk_load(ring + ipos + dep, p.entries + static_cast<size_t>(c_tile) * kBoxBlockBytes, n, bar);
+#ifdef BLINKY_LAB
+            else tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, (p.lab & 8u) ? 0 : static_cast<int>(c_frame), bar);
+#else
+            else tma_load_box(ring + ipos + dep, reinterpret_cast<const CUtensorMap *>(c_tmap), c_bx, c_by, c_plate, static_cast<int>(c_frame), bar);
+#endif
+        }
+        ipos += n;
         is = is + 1 == kRingBoxes ? 0 : is + 1;
         ++inflight;
-        ++c_frame;
+        if (c_entry) c_entry = false;
+        else ++c_frame;
         if (--c_left == 0) {
             ++c_unit;
             seat();
@@ -575,14 +566,18 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
             if (p.lab & 32u) a_bytes = p.lab_bytes;
 #endif
             // ---- the lane's 32 entries, out of the entry buffer into registers once for all frames of the unit
-            if (e_ticket != A.ticket) fetch_entries(A, 0);   // first unit of the warp, or the one after a GATHER unit
-            mbar_wait(ebar, e_phase);
-            e_phase ^= 1u;
+            mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
+            if (cpos + kBoxBlockBytes > R) cpos = 0;
+            const uint32_t ebuf = ring + cpos;
             uint4 eA[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) eA[k] = lds_v4(ebuf + (k * 32 + lane) * 16);
             uint32_t tintedA = 0;
             if (RUBIX) tintedA = lds_u32(ebuf + kBoxEntryBytes + lane * 4);
+            phases ^= 1u << cs;
+            cs = cs + 1 == kRingBoxes ? 0 : cs + 1;
+            cpos += kBoxBlockBytes;
+            --inflight;
             uint32_t off[32];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -599,15 +594,13 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
                 for (int i = 0; i < 32; ++i) off[i] = (lane * 4u + (i & 3) + (i >> 2) * 128u) & 1023u;
             }
 #endif
-            // the buffer is free once its words sit in registers (same reasoning as stage_dep): refill it with
-            // the block of the next BOX unit
+            // the block's bytes may be overwritten once they sit in registers (same reasoning as stage_dep)
             {
                 uint32_t dep = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dep |= eA[k].x | eA[k].y | eA[k].z | eA[k].w;
                 dep = (dep | tintedA) & p.zero;
-                if (is_box(B)) fetch_entries(B, dep);
-                else if (is_box(C)) fetch_entries(C, dep);
+                while (can_issue()) issue(dep);
             }
             // rubix overlay: one LUT row for the tile, a byte mask per quad of the pixels it applies to
             uint32_t tmask[8];
@@ -1217,23 +1210,24 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
     // Ring geometry: as many warps per SM as the registers allow (or BLINKY_RING_CTAS), each with the largest
     // staging ring that still lets that many CTAs share the SM's shared memory; fewer warps if the plan's
     // largest box would not fit such a ring.
-    const size_t fixed = kRingBarBytes + kBoxBlockBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
-    const uint32_t max_box = static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128);
+    const size_t fixed = kRingBarBytes + (rubix ? 6 * 256 : 0) + (rgba ? 1024 : 0);
+    const uint32_t max_box = std::max<uint32_t>(static_cast<uint32_t>(stage_bytes_ > 0 ? stage_bytes_ : 128), kBoxBlockBytes);  // largest ring item
     // (few gather items in absolute terms — short launches — also ride along: a second kernel launch costs more than they do)
     const uint32_t all_gather_items = ngather_tiles_ * (kTileH / kGatherRows) * static_cast<uint32_t>((nframes + kGatherFrames - 1) / kGatherFrames);
     const bool merged_gather = !serial_gather_ && ngather_tiles_ > 0 &&
                                (ngather_tiles_ * 100u <= ntiles_ * kMergedGatherPercent || all_gather_items <= static_cast<uint32_t>(merged_items_max_));
     int want = std::min(kRingWarpsDefault, rubix ? ring_warps<true>() : ring_warps<false>());
     if (ring_ctas_cap_ > 0) want = std::min(ring_ctas_cap_, rubix ? ring_warps<true>() : ring_warps<false>());
-    // ring size: twice the plan's largest box (two boxes of any size in flight; measured on the 4K panini plan, largest
-    // box 6.4 KB: 8 KB ring 5.2 us per frame, 12 KB 4.7), as far as `want` resident warps — plus two gather CTAs, which
+    // ring size: twice the plan's largest box plus an entry block (two boxes of any size and the next unit's entries in
+    // flight; measured on the 4K panini plan, largest box 6.4 KB: 8 KB ring 5.2 us per frame, 12 KB 4.7), as far as `want`
+    // resident warps — plus two gather CTAs, which
     // carry the same allocation, when GATHER tiles ride along — leave room in the SM's shared memory
     uint32_t ring_bytes = 0;
     for (; want >= 1; --want) {
         const size_t per_cta = smem_per_sm_ / static_cast<size_t>(want + (merged_gather ? 2 : 0));
         if (per_cta < 1024 + fixed + max_box) continue;
         const uint32_t room = static_cast<uint32_t>((per_cta - 1024 - fixed) / 128 * 128);
-        ring_bytes = std::min(room, std::max(2u * max_box, 8192u));
+        ring_bytes = std::min(room, std::max(2u * max_box + kBoxBlockBytes, 8192u));
         if (ring_bytes_override_ > 0) ring_bytes = std::min(room, std::max<uint32_t>(max_box, static_cast<uint32_t>(ring_bytes_override_) / 128 * 128));
         break;
     }
@@ -1242,7 +1236,10 @@ bool WarpDevice::launch_ring(const void *d_faces, size_t face_stride, void *d_ou
         return false;
     }
     p.ring_bytes = ring_bytes;
-    p.max_inflight = static_cast<uint32_t>(std::max(1, std::min(ring_boxes_, kRingBoxes)));
+    // items in flight per warp: two boxes and (at unit boundaries) the next entry block.  Measured: 2 / 3 / 4 the same on
+    // batches, and single-frame launches do not gain from running further ahead either (13.2 / 13.6 / 14.0 us with 2 / 4
+    // / 6) — they are bound by the ~480 instructions a unit costs, not by its loads (BLINKY_RING_BOXES overrides)
+    p.max_inflight = static_cast<uint32_t>(std::max(1, std::min(ring_boxes_ > 0 ? ring_boxes_ : 3, kRingBoxes)));
     const size_t smem = static_cast<size_t>(ring_bytes) + fixed;
     if (ring_ctas_per_sm_[vi] == 0 || ring_smem_[vi] != smem) {
         int n = 0;
