@@ -170,15 +170,16 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // takes work units (tile, chunk of frames) — most from a static schedule, the tail from a ticket
 // counter —, keeps the tile's lensmap entries in REGISTERS for all frames of the unit, and feeds
 // itself through a private ring of TMA tensor loads:
-//   * per unit: the tile's entry block (2 KB of 16-bit offsets) arrives by a bulk copy
-//     (cp.async.bulk) into the warp's entry buffer, issued a whole unit ahead; the lane reads its
-//     32 entries from there with four 128-bit shared loads and unpacks them once.
-//   * per frame: lane 0 has issued ONE 4-D TMA tensor load (x, y, plate, frame) of the tile's
-//     source box into the warp's byte ring, completing on an mbarrier; the warp waits, does 32
-//     byte loads from shared memory per lane (one per output pixel), packs them with PRMT into
-//     eight 32-bit words and writes them with streaming stores; the next box of the warp's
-//     sequence (this unit's later frames, then the next units' first frames) is issued as soon as
-//     the consumed box's bytes sit in registers.
+//   * the ring is a byte FIFO of items in shared memory: per unit its entry block (2 KB of 16-bit
+//     offsets, bulk copy cp.async.bulk) and then one source box per frame (ONE 4-D TMA tensor
+//     load: x, y, plate, frame), each completing on its own mbarrier, issued by lane 0 from a
+//     cursor that runs up to three units ahead.
+//   * per unit: the lane reads its 32 entries out of the ring with four 128-bit shared loads and
+//     unpacks them once.
+//   * per frame: the warp waits for the box, does 32 byte loads from shared memory per lane (one
+//     per output pixel), packs them with PRMT into eight 32-bit words, issues the next item(s) of
+//     its sequence as soon as the consumed bytes sit in registers, and writes the words with
+//     streaming stores.
 // There is no producer warp, no cross-warp barrier, no per-pixel entry traffic per frame, and no
 // global load on a scoreboard in the frame loop.  History, all measured (profiles/r2_c1*_sweep.jsonl):
 // round 1's kernel was bound by the serial per-item work of its producer thread; the first
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
 #ifdef BLINKY_LAB
             if (p.lab & 32u) a_bytes = p.lab_bytes;
 #endif
-            // ---- the lane's 32 entries, out of the entry buffer into registers once for all frames of the unit
+            // ---- the lane's 32 entries, out of the ring into registers once for all frames of the unit
             mbar_wait(bars + 8 * cs, (phases >> cs) & 1u);
             if (cpos + kBoxBlockBytes > R) cpos = 0;
             const uint32_t ebuf = ring + cpos;
