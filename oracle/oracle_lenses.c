@@ -589,6 +589,129 @@ static int cube_forward(double x, double y, double z, double *ox, double *oy, vo
 }
 
 /* ---- registry --------------------------------------------------------------- */
+/* ---- lenses/winkeltripel.lua ---------------------------------------------- */
+static double wt_lens_width, wt_lens_height, wt_artifact_x, wt_artifact_y; /* :82-94, set by wt_onload() */
+
+static int winkeltripel_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :9-21 */
+    (void)ud;
+    const double clat0 = 2 / pi; /* :2 */
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double clat = cos(lat);
+    double temp = clat * cos(lon * 0.5);
+    double D = acos(temp);
+    double C = 1 - temp * temp;
+    temp = D / sqrt(C);
+    *ox = 0.5 * (2 * temp * clat * sin(lon * 0.5) + lon * clat0);
+    *oy = 0.5 * (temp * sin(lat) + lat);
+    return 1;
+}
+
+static int winkeltripel_inverse(double x, double y, double o[3], void *ud)
+{ /* :25-80 — Newton iteration from d3-geo-projection's winkel3 */
+    (void)ud;
+    if (fabs(y) >= wt_lens_height / 2) return 0;
+    if (fabs(x) > wt_artifact_x && fabs(y) > wt_artifact_y) return 0; /* is_inside_artifact_box :93-95 */
+    double lambda = x, phi = y;
+    const double eps = 0.0001, halfpi = pi / 2;
+    for (int iter = 1; iter <= 25; ++iter) {
+        double cosphi = cos(phi);
+        double sinphi = sin(phi);
+        double sin_2phi = sin(2 * phi);
+        double sin2phi = sinphi * sinphi;
+        double cos2phi = cosphi * cosphi;
+        double sinlambda = sin(lambda);
+        double coslambda_2 = cos(lambda / 2);
+        double sinlambda_2 = sin(lambda / 2);
+        double sin2lambda_2 = sinlambda_2 * sinlambda_2;
+        double C = 1 - cos2phi * coslambda_2 * coslambda_2;
+        double E, F;
+        if (C != 0) {
+            F = 1 / C;
+            E = acos(cosphi * coslambda_2) * sqrt(F);
+        } else {
+            E = 0;
+            F = 0;
+        }
+        double fx = .5 * (2 * E * cosphi * sinlambda_2 + lambda / halfpi) - x;
+        double fy = .5 * (E * sinphi + phi) - y;
+        double sigxsiglambda = .5 * F * (cos2phi * sin2lambda_2 + E * cosphi * coslambda_2 * sin2phi) + .5 / halfpi;
+        double sigxsigphi = F * (sinlambda * sin_2phi / 4 - E * sinphi * sinlambda_2);
+        double sigysiglambda = .125 * F * (sin_2phi * sinlambda_2 - E * sinphi * cos2phi * sinlambda);
+        double sigysigphi = .5 * F * (sin2phi * coslambda_2 + E * sin2lambda_2 * cosphi) + .5;
+        double denominator = sigxsigphi * sigysiglambda - sigysigphi * sigxsiglambda;
+        double siglambda = (fy * sigxsigphi - fx * sigysigphi) / denominator;
+        double sigphi = (fx * sigysiglambda - fy * sigxsiglambda) / denominator;
+        lambda = lambda - siglambda;
+        phi = phi - sigphi;
+        if (fabs(siglambda) < eps && fabs(sigphi) < eps) break;
+    }
+    double lat = phi, lon = lambda;
+    double r[3], x0, y0;
+    orc_lua_latlon_to_ray(lat, pi, r); /* :75 lens_forward(latlon_to_ray(lat, pi)): the edge of the map at this latitude */
+    winkeltripel_forward(r[0], r[1], r[2], &x0, &y0, 0);
+    if (fabs(x) < fabs(x0)) {
+        orc_lua_latlon_to_ray(lat, lon, o);
+        return 1;
+    }
+    return 0;
+}
+
+static void wt_onload(void)
+{ /* :82-92 (chunk level) */
+    double r[3], x, y;
+    orc_lua_latlon_to_ray(pi / 2, 0, r);
+    winkeltripel_forward(r[0], r[1], r[2], &x, &y, 0);
+    wt_lens_height = 2 * y;
+    orc_lua_latlon_to_ray(0, pi, r);
+    winkeltripel_forward(r[0], r[1], r[2], &x, &y, 0);
+    wt_lens_width = 2 * x;
+    wt_artifact_x = wt_lens_width / 2 * 0.71;
+    wt_artifact_y = wt_lens_height / 2 * 0.81;
+}
+
+/* ---- lenses/eckert4.lua ---------------------------------------------------- */
+static double eckert4_solveTheta(double lat)
+{ /* :1-11 — 20 Newton steps */
+    double t = lat / 2, dt = 0;
+    for (int i = 1; i <= 20; ++i) {
+        dt = -(t + sin(t) * cos(t) + 2 * sin(t) - (2 + pi * 0.5) * sin(lat)) / (2 * cos(t) * (1 + cos(t)));
+        t = t + dt;
+    }
+    return t;
+}
+
+static double eckert4_maxy; /* :43 */
+
+static int eckert4_inverse(double x, double y, double o[3], void *ud)
+{ /* :22-31.  get_max_x (:13-20) caches maxx per value of y in script-level variables; maxx is a function of
+   * y alone (lat is), so computing it every time gives the same bits */
+    (void)ud;
+    double t = asin(y / 2 * sqrt((4 + pi) / pi));
+    double lat = asin((t + sin(t) * cos(t) + 2 * sin(t)) / (2 + pi * 0.5));
+    double lon = sqrt(pi * (4 + pi)) * x / (2 * (1 + cos(t)));
+    if (fabs(y) > eckert4_maxy) return 0;
+    {
+        double tt = eckert4_solveTheta(fabs(lat));
+        double maxx = 2 / sqrt(pi * (4 + pi)) * pi * (1 + cos(tt));
+        if (fabs(x) > maxx) return 0;
+    }
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int eckert4_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :33-39 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double t = eckert4_solveTheta(lat);
+    *ox = 2 / sqrt(pi * (4 + pi)) * lon * (1 + cos(t));
+    *oy = 2 * sqrt(pi / (4 + pi)) * sin(t);
+    return 1;
+}
+
 int orc_find_lens(const char *name, orc_lens_def *out)
 {
     memset(out, 0, sizeof *out);
@@ -629,6 +752,18 @@ int orc_find_lens(const char *name, orc_lens_def *out)
     } else if (!strcmp(name, "cube")) {
         out->inverse = cube_inverse; out->forward = cube_forward;
         out->max_fov = 360; out->max_vfov = 180; out->lens_width = 4; out->lens_height = 3; out->onload = "f_contain";
+    } else if (!strcmp(name, "winkeltripel")) {
+        wt_onload();
+        out->inverse = winkeltripel_inverse; out->forward = winkeltripel_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = wt_lens_width; out->lens_height = wt_lens_height; out->onload = "f_contain";
+    } else if (!strcmp(name, "eckert4")) {
+        double t = eckert4_solveTheta(pi * 0.5); /* :42-50 */
+        eckert4_maxy = 2 * sqrt(pi / (4 + pi)) * sin(t);
+        t = eckert4_solveTheta(0);
+        out->inverse = eckert4_inverse; out->forward = eckert4_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = 2 / sqrt(pi * (4 + pi)) * pi * (1 + cos(t)) * 2; out->lens_height = 2 * eckert4_maxy; out->onload = "f_contain";
     } else if (!strcmp(name, "fisheye2")) {
         double maxr = 2 * sin(pi * 0.5);
         out->inverse = fisheye2_inverse; out->forward = fisheye2_forward;

@@ -181,7 +181,8 @@ INVERSE_CB = ctypes.CFUNCTYPE(c_int, c_double, c_double, POINTER(c_double), c_vo
 FORWARD_CB = ctypes.CFUNCTYPE(c_int, c_double, c_double, c_double, POINTER(c_double), POINTER(c_double), c_void_p)
 
 TRANSCRIBED_LENSES = ["panini", "stereographic", "rectilinear", "equirect", "cylinder", "mercator", "hammer",
-                      "fisheye1", "fisheye2", "quincuncial", "sinusoidal", "winkel1", "mollweide", "vandergrinten", "cube"]
+                      "fisheye1", "fisheye2", "quincuncial", "sinusoidal", "winkel1", "mollweide", "vandergrinten", "cube",
+                      "winkeltripel", "eckert4"]
 TRANSCRIBED_GLOBES = ["cube", "trism", "tetra", "cube_edge", "cube_corner", "fast"]
 
 
