@@ -712,6 +712,247 @@ static int eckert4_forward(double x, double y, double z, double *ox, double *oy,
     return 1;
 }
 
+/* ---- lenses/miller.lua ------------------------------------------------------ */
+static double miller_maxy(void) { return 1.25 * log(tan(0.25 * pi + 0.4 * pi * 0.5)); } /* :1 */
+
+static int miller_inverse(double x, double y, double o[3], void *ud)
+{ /* :11-18 */
+    (void)ud;
+    if (fabs(y) > miller_maxy() || fabs(x) > pi) return 0;
+    double lon = x;
+    double lat = 5.0 / 4 * atan(sinh(4.0 / 5 * y));
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int miller_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :20-25 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon;
+    *oy = 1.25 * log(tan(0.25 * pi + 0.4 * lat));
+    return 1;
+}
+
+/* ---- lenses/gallstereo.lua -------------------------------------------------- */
+static const double gs_YF = 1.70710678118654752440, gs_XF = 0.70710678118654752440; /* :1-4 */
+static const double gs_RYF = 0.58578643762690495119, gs_RXF = 1.41421356237309504880;
+
+static int gallstereo_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :17-25 — the bounds test is on the ray's components, as written */
+    (void)ud;
+    const double maxx = gs_XF * pi, maxy = gs_YF * tan(0.5 * pi / 2);
+    if (fabs(x) > maxx || fabs(y) > maxy) return 0;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = gs_XF * lon;
+    *oy = gs_YF * tan(0.5 * lat);
+    return 1;
+}
+
+static int gallstereo_inverse(double x, double y, double o[3], void *ud)
+{ /* :27-31 */
+    (void)ud;
+    double lon = gs_RXF * x;
+    double lat = 2 * atan(y * gs_RYF);
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+/* ---- lenses/fahey.lua -------------------------------------------------------- */
+static int fahey_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :12-18 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double xx = tan(0.5 * lat);
+    double yy = 1.819152 * xx;
+    xx = 0.819152 * lon * sqrt(1 - xx * xx);
+    *ox = xx;
+    *oy = yy;
+    return 1;
+}
+
+static int fahey_inverse(double x, double y, double o[3], void *ud)
+{ /* :20-29 */
+    (void)ud;
+    const double XR = 0.819152 * pi, YR = 1.819152; /* :1-2 */
+    if (x * x / (XR * XR) + y * y / (YR * YR) >= 1) return 0;
+    y = y / 1.819152;
+    double lat = 2 * atan(y);
+    y = 1 - y * y;
+    double lon = x / (0.819152 * sqrt(y));
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+/* ---- forward-only lenses ------------------------------------------------------ */
+static int eckert1_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* eckert1.lua:15-20 */
+    (void)ud;
+    const double FC = 0.92131773192356127802, RP = 0.31830988618379067154;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = FC * lon * (1 - RP * fabs(lat));
+    *oy = FC * lat;
+    return 1;
+}
+
+static int eckert5_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* eckert5.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon * (1 + cos(lat)) / 2;
+    *oy = lat;
+    return 1;
+}
+
+static int kavrayskiy7_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* kavrayskiy7.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = 3 * lon / (2 * pi) * sqrt(pi * pi / 3 - lat * lat);
+    *oy = lat;
+    return 1;
+}
+
+static int winkel2_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* winkel2.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon / 2 * (2 / pi + sqrt(pi * pi - 4 * lat * lat) / pi);
+    *oy = lat;
+    return 1;
+}
+
+static int wagner6_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* wagner6.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = lon * sqrt(1 - 3 * lat * lat / (pi * pi));
+    *oy = lat;
+    return 1;
+}
+
+static int larrivee_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* larrivee.lua:10-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    *ox = (0.5 + 0.5 * sqrt(cos(lat))) * lon;
+    *oy = lat / (cos(lat / 2) * cos(lon / 6));
+    return 1;
+}
+
+static int gins8_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* gins8.lua:10-20 */
+    (void)ud;
+    const double Cl = 0.000952426, Cp = 0.162388, C12 = 0.08333333333333333;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    double t = lat * lat;
+    double yy = lat * (1 + t * C12);
+    double xx = lon * (1 - Cp * t);
+    t = lon * lon;
+    xx = xx * (0.87 - Cl * t * t);
+    *ox = xx;
+    *oy = yy;
+    return 1;
+}
+
+/* ---- lenses/cubestereo.lua -------------------------------------------------- */
+static int cubestereo_forward(double rx, double ry, double rz, double *ox, double *oy, void *ud)
+{ /* projectcube :6-19, lens_forward :21-24 */
+    (void)ud;
+    double magx = fabs(rx), magy = fabs(ry), magz = fabs(rz);
+    double mag = magz;
+    if (magx >= magy && magx >= magz) mag = magx;
+    else if (magy >= magx && magy >= magz) mag = magy;
+    double x = rx / mag, y = ry / mag, z = rz / mag;
+    *ox = x / (z + 1) * 2;
+    *oy = y / (z + 1) * 2;
+    return 1;
+}
+
+static int cubestereo_inverse(double x, double y, double o[3], void *ud)
+{ /* :26-50 — returns the ray itself, not latlon_to_ray() */
+    (void)ud;
+    double rx, ry, rz;
+    double magx = fabs(x), magy = fabs(y), z = 2;
+    if (magx <= 1 && magy <= 1) {
+        rx = x;
+        ry = y;
+        rz = z - 1;
+    } else if (magx > magy) {
+        rx = x / magx;
+        ry = y / magx;
+        rz = z / magx - 1;
+    } else {
+        rx = x / magy;
+        ry = y / magy;
+        rz = z / magy - 1;
+    }
+    double len = sqrt(rx * rx + ry * ry + rz * rz);
+    o[0] = rx / len;
+    o[1] = ry / len;
+    o[2] = rz / len;
+    return 1;
+}
+
+/* ---- lenses/polyconic.lua --------------------------------------------------- */
+static int polyconic_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :7-15 */
+    (void)ud;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    if (lat == 0) {
+        *ox = lon;
+        *oy = 0;
+        return 1;
+    }
+    *ox = 1 / tan(lat) * sin(lon * sin(lat));
+    *oy = lat + 1 / tan(lat) * (1 - cos(lon * sin(lat)));
+    return 1;
+}
+
+/* ---- lenses/gumby.lua -------------------------------------------------------- */
+static const double gumby_d = 1, gumbyScale = 0.75; /* :1-2 */
+
+static int gumby_inverse(double x, double y, double o[3], void *ud)
+{ /* :10-20 */
+    (void)ud;
+    const double d = gumby_d, gumbyScaleInv = 1.0 / gumbyScale; /* :3 */
+    double k = x * x / ((d + 1) * (d + 1));
+    double dscr = k * k * d * d - (k + 1) * (k * d * d - 1);
+    double clon = (-k * d + sqrt(dscr)) / (k + 1);
+    double S = (d + 1) / (d + clon);
+    double lon = atan2(x, S * clon);
+    double lat = atan2(y, S);
+    lon = lon * gumbyScaleInv;
+    lat = lat * gumbyScaleInv;
+    orc_lua_latlon_to_ray(lat, lon, o);
+    return 1;
+}
+
+static int gumby_forward(double x, double y, double z, double *ox, double *oy, void *ud)
+{ /* :22-30 */
+    (void)ud;
+    const double d = gumby_d;
+    double lat, lon;
+    orc_lua_ray_to_latlon(x, y, z, &lat, &lon);
+    lon = lon * gumbyScale;
+    lat = lat * gumbyScale;
+    double S = (d + 1) / (d + cos(lon));
+    *ox = S * sin(lon);
+    *oy = S * tan(lat);
+    return 1;
+}
+
 int orc_find_lens(const char *name, orc_lens_def *out)
 {
     memset(out, 0, sizeof *out);
@@ -764,6 +1005,61 @@ int orc_find_lens(const char *name, orc_lens_def *out)
         out->inverse = eckert4_inverse; out->forward = eckert4_forward;
         out->max_fov = 360; out->max_vfov = 180;
         out->lens_width = 2 / sqrt(pi * (4 + pi)) * pi * (1 + cos(t)) * 2; out->lens_height = 2 * eckert4_maxy; out->onload = "f_contain";
+    } else if (!strcmp(name, "miller")) {
+        out->inverse = miller_inverse; out->forward = miller_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->lens_height = miller_maxy() * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "gallstereo")) {
+        out->inverse = gallstereo_inverse; out->forward = gallstereo_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = gs_XF * pi * 2; out->lens_height = gs_YF * tan(0.5 * pi / 2) * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "fahey")) {
+        out->inverse = fahey_inverse; out->forward = fahey_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 0.819152 * pi * 2; out->lens_height = 1.819152 * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "eckert1")) {
+        out->forward = eckert1_forward;
+        out->max_fov = 360; out->max_vfov = 180;
+        out->lens_width = 0.92131773192356127802 * pi * 2; out->lens_height = 0.92131773192356127802 * pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "eckert5")) {
+        out->forward = eckert5_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = pi * 2; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "kavrayskiy7")) {
+        out->forward = kavrayskiy7_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 3 * pi / (2 * pi) * sqrt(pi * pi / 3) * 2; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "winkel2")) {
+        out->forward = winkel2_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = pi / 2 * (2 / pi + 1) * 2; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "wagner6")) {
+        out->forward = wagner6_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = pi * 2; out->lens_height = pi; out->onload = "f_contain";
+    } else if (!strcmp(name, "larrivee")) {
+        out->forward = larrivee_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->lens_width = 2 * pi; out->lens_height = pi / 2 / cos(pi / 2 / 2) * 2; out->onload = "f_contain";
+    } else if (!strcmp(name, "gins8")) {
+        double r[3], x, y;
+        out->forward = gins8_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->onload = "f_contain";
+        orc_lua_latlon_to_ray(0, pi, r);   /* :22-25 (chunk level) */
+        gins8_forward(r[0], r[1], r[2], &x, &y, 0);
+        out->lens_width = 2 * fabs(x);
+        orc_lua_latlon_to_ray(pi / 2, 0, r);
+        gins8_forward(r[0], r[1], r[2], &x, &y, 0);
+        out->lens_height = 2 * fabs(y);
+    } else if (!strcmp(name, "cubestereo")) {
+        out->inverse = cubestereo_inverse; out->forward = cubestereo_forward;
+        out->max_fov = 270; out->max_vfov = 270; out->onload = "f_fov 180";
+    } else if (!strcmp(name, "polyconic")) {
+        out->forward = polyconic_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->onload = "f_fov 360";
+    } else if (!strcmp(name, "gumby")) {
+        double r[3], x, y;
+        out->inverse = gumby_inverse; out->forward = gumby_forward;
+        out->max_fov = 360; out->max_vfov = 180; out->onload = "f_contain";
+        orc_lua_latlon_to_ray(pi / 2, 0, r);   /* :32-36 (chunk level) */
+        gumby_forward(r[0], r[1], r[2], &x, &y, 0);
+        out->lens_height = y * 2;
+        orc_lua_latlon_to_ray(0, pi, r);
+        gumby_forward(r[0], r[1], r[2], &x, &y, 0);
+        out->lens_width = x * 2;
     } else if (!strcmp(name, "fisheye2")) {
         double maxr = 2 * sin(pi * 0.5);
         out->inverse = fisheye2_inverse; out->forward = fisheye2_forward;

@@ -182,7 +182,8 @@ FORWARD_CB = ctypes.CFUNCTYPE(c_int, c_double, c_double, c_double, POINTER(c_dou
 
 TRANSCRIBED_LENSES = ["panini", "stereographic", "rectilinear", "equirect", "cylinder", "mercator", "hammer",
                       "fisheye1", "fisheye2", "quincuncial", "sinusoidal", "winkel1", "mollweide", "vandergrinten", "cube",
-                      "winkeltripel", "eckert4"]
+                      "winkeltripel", "eckert4", "miller", "gallstereo", "fahey", "eckert1", "eckert5", "kavrayskiy7", "winkel2",
+                      "wagner6", "larrivee", "gins8", "polyconic", "gumby", "cubestereo"]
 TRANSCRIBED_GLOBES = ["cube", "trism", "tetra", "cube_edge", "cube_corner", "fast"]
 
 
