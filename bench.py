@@ -9,12 +9,20 @@ step     one pass of the hot path over one batch of FRAMES distinct synthetic fr
          (one kernel launch).  The frames of a batch are 16 x 25 MB = 403 MB of faces, larger
          than the 126 MB L2, so every step streams its faces from HBM; the lensmap (static per
          lens, like the reference's) is reused by all frames and stays L2-resident.
-value    whole-job throughput over all N GPUs with inputs resident in HBM (CUDA events on the
-         launch stream, max over ranks).  Frames are independent: rank r warps its own batch,
-         no collective on the data path ("weak" scaling); the NCCL gather of finished frames
-         to rank 0 that the reference topology needs is timed separately (key "gather").
+value    N = 1: throughput with inputs resident in HBM (CUDA events on the launch stream).  N > 1: frames are
+         independent — rank r warps its own batch, no collective on the data path ("weak" scaling;
+         `value_warp_only` is that aggregate) — and the reference topology's last step, finished frames to the
+         one display, is a gather to rank 0 through the C ABI (blinky_shard_warp_gather: NCCL send/recv,
+         copy-engine peer copies or in-kernel peer stores, overlapped with the warp): `value` is the
+         DELIVERED-TO-RANK-0 rate of the fastest transport (all three are timed and compared, key "gather"),
+         max over ranks.
 e2e      the same metric through the C ABI's host entry point blinky_warp_host: pinned host
-         faces -> cudaMemcpyAsync -> warp -> copy back, all inside the timed region.
+         faces -> batched async copies -> warp -> copy back, all inside the timed region.
+roofline frac = SURVEY 8(d) algorithmic bytes / launch time / measured HBM peak; compulsory_frac = bytes the
+         launch cannot avoid (counted from the lensmap in this run); dram_frac = ncu-measured DRAM bytes of
+         this workload's launch (profiles/traffic_r2.json) / this run's launch time.
+secondary  every other BASELINE configuration (C2, C3, the C4 lenses, C5 trism/cube): batched and single
+         cold frame, same three fractions.
 --impl reference   the reference's own CPU loop (oracle/_ref = unmodified fisheye.c compiled
          headless; else the oracle port) on the host cores, same workload, bounded sample.
 
