@@ -870,7 +870,9 @@ struct WarpDevice::Slot {
     uint8_t *h_faces = nullptr, *h_out = nullptr;  // pinned staging
     bool busy = false;
     // finalize info
-    uint8_t *dst = nullptr;
+    uint8_t *dst = nullptr;          // first frame of the group
+    size_t dst_frame_stride = 0;
+    int nf = 0;                      // frames in the slot
     int dst_rowbytes = 0, x0 = 0, y0 = 0;
     bool keep_unmapped = false, direct = false;
 };
@@ -1395,6 +1397,14 @@ bool WarpDevice::ensure_slots() {
         const int v = atoi(e);
         if (v >= 1 && v <= 16) kSlots = v;
     }
+    // A slot can hold a GROUP of frames (one batched upload, one launch, one copy back per group; BLINKY_HOST_GROUP).
+    // Measured with 16-frame calls: 1 / 2 / 4 / 8 frames per group give 28.4 / 26.6 / 25.9 / 25.0 Gpx/s — fewer, larger
+    // copies do not make the link faster, and the coarser pipeline overlaps less — so the default is one frame per slot.
+    host_group_ = 1;
+    if (const char *e = getenv("BLINKY_HOST_GROUP")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxHostGroup) host_group_ = v;
+    }
     slot_face_bytes_ = static_cast<size_t>(numplates_) * platesize_ * platesize_;
     slot_out_bytes_ = round_up(npix_, 16);
     for (int i = 0; i < kSlots; ++i) {
@@ -1402,11 +1412,10 @@ bool WarpDevice::ensure_slots() {
         slots_.push_back(s);
         CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
-        CK(cudaMalloc(&s->d_faces, slot_face_bytes_));
-        CK(cudaMemset(s->d_faces, 0, slot_face_bytes_));
-        CK(cudaMalloc(&s->d_out, slot_out_bytes_));
-        CK(cudaMallocHost(&s->h_faces, slot_face_bytes_));
-        CK(cudaMallocHost(&s->h_out, slot_out_bytes_));
+        CK(cudaMalloc(&s->d_faces, slot_face_bytes_ * host_group_));
+        CK(cudaMemset(s->d_faces, 0, slot_face_bytes_ * host_group_));
+        CK(cudaMalloc(&s->d_out, slot_out_bytes_ * host_group_));
+        // (pinned staging for callers whose buffers are not pinned: allocated when first needed)
     }
     return true;
 }
@@ -1417,21 +1426,24 @@ void WarpDevice::finalize_slot(Slot &s) {
     s.busy = false;
     if (s.direct) return;  // the copy engine already wrote the caller's buffer
     const int W = width_, H = height_;
-    uint8_t *dst = s.dst + static_cast<size_t>(s.y0) * s.dst_rowbytes + s.x0;
-    if (s.keep_unmapped) {
-        // only mapped pixels are written, like `if (*lmap)` in render_lensmap (:2413)
-        for (int y = 0; y < H; ++y) {
-            const uint8_t *src = s.h_out + static_cast<size_t>(y) * W;
-            uint8_t *row = dst + static_cast<size_t>(y) * s.dst_rowbytes;
-            for (int32_t k = span_off_[static_cast<size_t>(y)]; k < span_off_[static_cast<size_t>(y) + 1]; ++k) {
-                const int32_t a = spans_[static_cast<size_t>(k) * 2], b = spans_[static_cast<size_t>(k) * 2 + 1];
-                memcpy(row + a, src + a, static_cast<size_t>(b - a));
+    for (int k = 0; k < s.nf; ++k) {
+        uint8_t *dst = s.dst + static_cast<size_t>(k) * s.dst_frame_stride + static_cast<size_t>(s.y0) * s.dst_rowbytes + s.x0;
+        const uint8_t *frame = s.h_out + static_cast<size_t>(k) * slot_out_bytes_;
+        if (s.keep_unmapped) {
+            // only mapped pixels are written, like `if (*lmap)` in render_lensmap (:2413)
+            for (int y = 0; y < H; ++y) {
+                const uint8_t *src = frame + static_cast<size_t>(y) * W;
+                uint8_t *row = dst + static_cast<size_t>(y) * s.dst_rowbytes;
+                for (int32_t j = span_off_[static_cast<size_t>(y)]; j < span_off_[static_cast<size_t>(y) + 1]; ++j) {
+                    const int32_t a = spans_[static_cast<size_t>(j) * 2], b = spans_[static_cast<size_t>(j) * 2 + 1];
+                    memcpy(row + a, src + a, static_cast<size_t>(b - a));
+                }
             }
+        } else if (s.dst_rowbytes == W) {
+            memcpy(dst, frame, static_cast<size_t>(W) * H);
+        } else {
+            for (int y = 0; y < H; ++y) memcpy(dst + static_cast<size_t>(y) * s.dst_rowbytes, frame + static_cast<size_t>(y) * W, static_cast<size_t>(W));
         }
-    } else if (s.dst_rowbytes == W) {
-        memcpy(dst, s.h_out, static_cast<size_t>(W) * H);
-    } else {
-        for (int y = 0; y < H; ++y) memcpy(dst + static_cast<size_t>(y) * s.dst_rowbytes, s.h_out + static_cast<size_t>(y) * W, static_cast<size_t>(W));
     }
 }
 
@@ -1460,69 +1472,84 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
     const bool src_pinned = pin_src_, dst_pinned = pin_dst_;
     const int W = width_, H = height_;
     bool ok = true;
-    for (int f = 0; f < nframes && ok; ++f) {
-        Slot &s = *slots_[static_cast<size_t>(f) % slots_.size()];
-        finalize_slot(s);  // frees the slot (waits for frame f-3)
-        const uint8_t *src = faces_host + static_cast<size_t>(f) * face_stride;
+    const int G = std::max(1, std::min(host_group_, kMaxHostGroup));
+    int group = 0;
+    for (int f0 = 0; f0 < nframes && ok; ++group) {
+        const int g = std::min(G, nframes - f0);
+        Slot &s = *slots_[static_cast<size_t>(group) % slots_.size()];
+        finalize_slot(s);  // frees the slot (waits for the group that used it last)
+        const bool direct = dst_pinned && !keep_unmapped;
+        if (!src_pinned && !s.h_faces) CK(cudaMallocHost(&s.h_faces, slot_face_bytes_ * G));
+        if (!direct && !s.h_out) CK(cudaMallocHost(&s.h_out, slot_out_bytes_ * G));
         // Only what the lens looks at is uploaded: plates with display != 0 (:764-766), and of
         // those only the texel rectangle the lensmap samples.  (TMA boxes may overhang the
         // rectangle; those texels are staged but never referenced by an entry.)
-        UploadRects ur;
-        ur.n = 0;
-        ur.first[0] = 0;
-        ur.pitch = static_cast<uint32_t>(platesize_);
-        const bool by_kernel = upload_by_kernel_ && platesize_ % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 && face_stride % 16 == 0;
-        cudaMemcpy3DBatchOp ops[BLINKY_MAX_PLATES];
+        cudaMemcpy3DBatchOp ops[BLINKY_MAX_PLATES * kMaxHostGroup];
         size_t nops = 0;
-        for (int pl = 0; pl < numplates_; ++pl) {
-            if (!display_[pl]) continue;
-            const int *r = plate_rect_[pl];
-            if (r[0] > r[2] || r[1] > r[3]) continue;
-            if (by_kernel && src_pinned) {
-                const int xa = r[0] & ~15, xb = (r[2] + 16) & ~15;  // 16-byte columns covering [r0, r2]
-                ur.off[ur.n] = static_cast<uint32_t>(pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + xa);
-                ur.vec_w[ur.n] = static_cast<uint32_t>((xb - xa) / 16);
-                ur.rows[ur.n] = static_cast<uint32_t>(r[3] - r[1] + 1);
-                ur.first[ur.n + 1] = ur.first[ur.n] + ur.vec_w[ur.n] * ur.rows[ur.n];
-                ++ur.n;
-                continue;
+        for (int k = 0; k < g && ok; ++k) {
+            const uint8_t *src = faces_host + static_cast<size_t>(f0 + k) * face_stride;
+            uint8_t *d_frame = s.d_faces + static_cast<size_t>(k) * slot_face_bytes_;
+            UploadRects ur;
+            ur.n = 0;
+            ur.first[0] = 0;
+            ur.pitch = static_cast<uint32_t>(platesize_);
+            const bool by_kernel = upload_by_kernel_ && platesize_ % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 && face_stride % 16 == 0;
+            for (int pl = 0; pl < numplates_; ++pl) {
+                if (!display_[pl]) continue;
+                const int *r = plate_rect_[pl];
+                if (r[0] > r[2] || r[1] > r[3]) continue;
+                if (by_kernel && src_pinned) {
+                    const int xa = r[0] & ~15, xb = (r[2] + 16) & ~15;  // 16-byte columns covering [r0, r2]
+                    ur.off[ur.n] = static_cast<uint32_t>(pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + xa);
+                    ur.vec_w[ur.n] = static_cast<uint32_t>((xb - xa) / 16);
+                    ur.rows[ur.n] = static_cast<uint32_t>(r[3] - r[1] + 1);
+                    ur.first[ur.n + 1] = ur.first[ur.n] + ur.vec_w[ur.n] * ur.rows[ur.n];
+                    ++ur.n;
+                    continue;
+                }
+                const size_t rw = static_cast<size_t>(r[2] - r[0] + 1), rh = static_cast<size_t>(r[3] - r[1] + 1);
+                const size_t off = pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + r[0];
+                const uint8_t *from = src + off;
+                if (!src_pinned) {
+                    uint8_t *stage = s.h_faces + static_cast<size_t>(k) * slot_face_bytes_ + off;
+                    for (size_t y = 0; y < rh; ++y) memcpy(stage + y * platesize_, from + y * platesize_, rw);
+                    from = stage;
+                }
+                // a full-width rectangle is one contiguous run: copy it as such
+                const bool contiguous = rw == static_cast<size_t>(platesize_);
+                if (batch_copies_) {  // all rectangles of the group in ONE driver call (no gap between the DMA operations)
+                    cudaMemcpy3DBatchOp &op = ops[nops++];
+                    memset(&op, 0, sizeof op);
+                    const size_t row = contiguous ? rw * rh : static_cast<size_t>(platesize_), rows = contiguous ? 1 : rh;
+                    op.src.type = cudaMemcpyOperandTypePointer;
+                    op.src.op.ptr.ptr = const_cast<uint8_t *>(from);
+                    op.src.op.ptr.rowLength = row;
+                    op.src.op.ptr.layerHeight = rows;
+                    op.dst.type = cudaMemcpyOperandTypePointer;
+                    op.dst.op.ptr.ptr = d_frame + off;
+                    op.dst.op.ptr.rowLength = row;
+                    op.dst.op.ptr.layerHeight = rows;
+                    op.extent = make_cudaExtent(contiguous ? rw * rh : rw, rows, 1);
+                    op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                    continue;
+                }
+                cudaError_t e = contiguous ? cudaMemcpyAsync(d_frame + off, from, rw * rh, cudaMemcpyHostToDevice, s.stream)
+                                           : cudaMemcpy2DAsync(d_frame + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
+                                                               cudaMemcpyHostToDevice, s.stream);
+                if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
             }
-            const size_t rw = static_cast<size_t>(r[2] - r[0] + 1), rh = static_cast<size_t>(r[3] - r[1] + 1);
-            const size_t off = pl * ps2 + static_cast<size_t>(r[1]) * platesize_ + r[0];
-            const uint8_t *from = src + off;
-            if (!src_pinned) {
-                for (size_t y = 0; y < rh; ++y) memcpy(s.h_faces + off + y * platesize_, from + y * platesize_, rw);
-                from = s.h_faces + off;
+            if (ok && ur.n > 0) {
+                const uint32_t total = ur.first[ur.n];
+                const unsigned blocks = std::min<unsigned>((total + 255) / 256, static_cast<unsigned>(sm_count_) * 8u);
+                upload_rects_kernel<<<blocks, 256, 0, s.stream>>>(src, d_frame, ur);
+                ++launches_;
             }
-            // a full-width rectangle is one contiguous run: copy it as such (the DMA engines move long runs faster than
-            // pitched rows)
-            const bool contiguous = rw == static_cast<size_t>(platesize_);
-            if (batch_copies_) {  // all rectangles of the frame in ONE driver call (no gap between six DMA operations)
-                cudaMemcpy3DBatchOp &op = ops[nops++];
-                memset(&op, 0, sizeof op);
-                const size_t row = contiguous ? rw * rh : static_cast<size_t>(platesize_), rows = contiguous ? 1 : rh;
-                op.src.type = cudaMemcpyOperandTypePointer;
-                op.src.op.ptr.ptr = const_cast<uint8_t *>(from);
-                op.src.op.ptr.rowLength = row;
-                op.src.op.ptr.layerHeight = rows;
-                op.dst.type = cudaMemcpyOperandTypePointer;
-                op.dst.op.ptr.ptr = s.d_faces + off;
-                op.dst.op.ptr.rowLength = row;
-                op.dst.op.ptr.layerHeight = rows;
-                op.extent = make_cudaExtent(contiguous ? rw * rh : rw, rows, 1);
-                op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-                continue;
-            }
-            cudaError_t e = contiguous ? cudaMemcpyAsync(s.d_faces + off, from, rw * rh, cudaMemcpyHostToDevice, s.stream)
-                                       : cudaMemcpy2DAsync(s.d_faces + off, static_cast<size_t>(platesize_), from, static_cast<size_t>(platesize_), rw, rh,
-                                                           cudaMemcpyHostToDevice, s.stream);
-            if (e != cudaSuccess) { ok = fail("cudaMemcpy2DAsync(H2D faces)", e); break; }
         }
         if (ok && nops > 0) {
             size_t fail_idx = 0;
             cudaError_t e = cudaMemcpy3DBatchAsync(nops, ops, &fail_idx, 0, s.stream);
             if (e != cudaSuccess) {
-                // not available on this driver: fall back to one 2-D copy per plate, from now on
+                // not available on this driver: fall back to one copy per rectangle, from now on
                 cudaGetLastError();
                 batch_copies_ = false;
                 for (size_t k = 0; k < nops && ok; ++k) {
@@ -1532,43 +1559,46 @@ bool WarpDevice::warp_host(const uint8_t *faces_host, size_t face_stride, uint8_
                 }
             }
         }
-        if (ok && ur.n > 0) {
-            const uint32_t total = ur.first[ur.n];
-            const unsigned blocks = std::min<unsigned>((total + 255) / 256, static_cast<unsigned>(sm_count_) * 8u);
-            upload_rects_kernel<<<blocks, 256, 0, s.stream>>>(src, s.d_faces, ur);
-            ++launches_;
-        }
         if (!ok) break;
-        s.dst = dst_host + static_cast<size_t>(f) * dst_frame_stride;
-        // the warp kernel can store straight into the caller's pinned frame (posted PCIe writes, no
-        // staging copy) when the frame is tightly packed
-        const bool zero_copy_out = out_by_kernel_ && dst_pinned && !keep_unmapped && dst_rowbytes == W && x0 == 0 && y0 == 0 &&
-                                   reinterpret_cast<uintptr_t>(s.dst) % 16 == 0;
-        if (!warp(s.d_faces, slot_face_bytes_, zero_copy_out ? s.dst : s.d_out, slot_out_bytes_, 1, s.stream, false)) { ok = false; break; }
+        s.dst = dst_host + static_cast<size_t>(f0) * dst_frame_stride;
+        s.dst_frame_stride = dst_frame_stride;
+        s.nf = g;
+        // the warp kernel can store straight into the caller's pinned frames (posted PCIe writes, no
+        // staging copy) when they are tightly packed
+        const bool zero_copy_out = out_by_kernel_ && direct && dst_rowbytes == W && x0 == 0 && y0 == 0 &&
+                                   reinterpret_cast<uintptr_t>(s.dst) % 16 == 0 && (g == 1 || dst_frame_stride % 16 == 0);
+        if (!warp(s.d_faces, slot_face_bytes_, zero_copy_out ? s.dst : s.d_out, zero_copy_out ? dst_frame_stride : slot_out_bytes_, g, s.stream, false)) { ok = false; break; }
         s.dst_rowbytes = dst_rowbytes;
         s.x0 = x0;
         s.y0 = y0;
         s.keep_unmapped = keep_unmapped;
-        s.direct = dst_pinned && !keep_unmapped;
-        cudaError_t e;
+        s.direct = direct;
+        cudaError_t e = cudaSuccess;
+        const size_t frame = static_cast<size_t>(W) * H;
         if (zero_copy_out) {
-            e = cudaSuccess;
-        } else if (s.direct && dst_rowbytes == W) {   // a tightly packed destination: one contiguous run
-            e = cudaMemcpyAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, s.d_out, static_cast<size_t>(W) * H, cudaMemcpyDeviceToHost, s.stream);
-        } else if (s.direct) {
-            e = cudaMemcpy2DAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, static_cast<size_t>(dst_rowbytes), s.d_out,
-                                  static_cast<size_t>(W), static_cast<size_t>(W), static_cast<size_t>(H), cudaMemcpyDeviceToHost, s.stream);
+        } else if (direct && dst_rowbytes == W && (g == 1 || (dst_frame_stride == frame && slot_out_bytes_ == frame))) {
+            // tightly packed destination frames: the whole group is one contiguous run
+            e = cudaMemcpyAsync(s.dst + static_cast<size_t>(y0) * dst_rowbytes + x0, s.d_out, frame * g, cudaMemcpyDeviceToHost, s.stream);
+        } else if (direct) {
+            for (int k = 0; k < g && e == cudaSuccess; ++k) {
+                uint8_t *to = s.dst + static_cast<size_t>(k) * dst_frame_stride + static_cast<size_t>(y0) * dst_rowbytes + x0;
+                const uint8_t *from = s.d_out + static_cast<size_t>(k) * slot_out_bytes_;
+                e = dst_rowbytes == W ? cudaMemcpyAsync(to, from, frame, cudaMemcpyDeviceToHost, s.stream)
+                                      : cudaMemcpy2DAsync(to, static_cast<size_t>(dst_rowbytes), from, static_cast<size_t>(W), static_cast<size_t>(W),
+                                                          static_cast<size_t>(H), cudaMemcpyDeviceToHost, s.stream);
+            }
         } else {
-            e = cudaMemcpyAsync(s.h_out, s.d_out, static_cast<size_t>(W) * H, cudaMemcpyDeviceToHost, s.stream);
+            e = cudaMemcpyAsync(s.h_out, s.d_out, slot_out_bytes_ * (g - 1) + frame, cudaMemcpyDeviceToHost, s.stream);
         }
         if (e != cudaSuccess) { ok = fail("cudaMemcpyAsync(D2H frame)", e); break; }
         e = cudaEventRecord(s.done, s.stream);
         if (e != cudaSuccess) { ok = fail("cudaEventRecord", e); break; }
         s.busy = true;
+        f0 += g;
     }
     // drain in submission order
     for (size_t k = 0; k < slots_.size(); ++k) {
-        Slot &s = *slots_[(static_cast<size_t>(nframes) + k) % slots_.size()];
+        Slot &s = *slots_[(static_cast<size_t>(group) + k) % slots_.size()];
         finalize_slot(s);
     }
     if (ok) {

@@ -133,6 +133,8 @@ private:
     // e2e pipeline
     std::vector<Slot *> slots_;
     size_t slot_face_bytes_ = 0, slot_out_bytes_ = 0;
+    static constexpr int kMaxHostGroup = 8;
+    int host_group_ = 1;                 // frames per slot of the blinky_warp_host pipeline (BLINKY_HOST_GROUP)
 
     int64_t launches_ = 0;
     std::string last_kernel_;
