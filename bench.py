@@ -292,6 +292,22 @@ def time_device(torch, fe, d_faces, d_out, frames, steps, warmup, stream, flush=
     return float(np.median(ts))
 
 
+def time_single_frame_stream(torch, fe, d_faces, d_out, stream, rounds=3):
+    """seconds per single-frame launch when every launch warps a different frame (the engine's call pattern)"""
+    F = d_faces.shape[0]
+    for i in range(F):  # warm-up: builds the per-pointer TMA descriptors
+        fe.warp(d_faces[i:], d_out[i:], nframes=1, stream=stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        for i in range(F):
+            fe.warp(d_faces[i:], d_out[i:], nframes=1, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (rounds * F)
+
+
 def roofline_entry(fe, launch_s, frames, peak, traffic):
     npix, M = fe.width * fe.height, fe.mapped_pixels
     alg = (5 * npix + M) * frames  # SURVEY section 8d: 4 B lensmap entry + 1 B source (mapped) + 1 B output per pixel
@@ -618,6 +634,11 @@ def run_secondary(args, torch, bb, fe, peak, traffic_db, stream):
         tc = time_device(torch, fe, d_faces, d_out, 1, 7, 3, stream, flush=flush)
         row["single_frame_cold"] = {"us": round(tc * 1e6, 2), "value": round(W * H / tc / 1e6, 1),
                                     "roofline": roofline_entry(fe, tc, 1, peak, None)}
+        ts = time_single_frame_stream(torch, fe, d_faces, d_out, stream)
+        row["single_frame_stream"] = {"us": round(ts * 1e6, 2), "value": round(W * H / ts / 1e6, 1),
+                                      "roofline": roofline_entry(fe, ts, 1, peak, None),
+                                      "how": "single-frame launches back to back, each on a different frame of the batch: the faces miss "
+                                             "L2 (F x 25 MB > 126 MB), the tile plan stays resident — the in-engine shape"}
         rows.append(row)
         del d_faces, d_out
     return rows
