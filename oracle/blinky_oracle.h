@@ -120,6 +120,8 @@ typedef struct {
     const char *onload;
 } orc_lens_def;
 int orc_find_lens(const char *name, orc_lens_def *out);
+/* lenses/debug.lua sizes itself from the globe's plate count and needs the globe as `ud` of its inverse */
+int orc_debug_lens(int numplates, orc_lens_def *out);
 /* name: "cube","trism","tetra","cube_edge","cube_corner","fast" */
 int orc_load_globe(const char *name, orc_globe *g);
 

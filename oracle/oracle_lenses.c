@@ -904,6 +904,40 @@ static int cubestereo_inverse(double x, double y, double o[3], void *ud)
     return 1;
 }
 
+/* ---- lenses/debug.lua --------------------------------------------------------
+ * The one lens that reads `numplates` and calls plate_to_ray: `ud` is the globe (orc_globe *), and
+ * orc_debug_lens() must have been called with its numplates (the script's chunk-level code, :1-17). */
+static int debug_rows = 1;
+static double debug_cols[2] = {0, 0};
+
+int orc_debug_lens(int numplates, orc_lens_def *out)
+{
+    if (numplates == 4) { debug_rows = 2; debug_cols[0] = 2; debug_cols[1] = 2; }
+    else if (numplates == 5) { debug_rows = 2; debug_cols[0] = 3; debug_cols[1] = 2; }
+    else if (numplates == 6) { debug_rows = 2; debug_cols[0] = 3; debug_cols[1] = 3; }
+    else { debug_rows = 1; debug_cols[0] = numplates; debug_cols[1] = 0; }
+    double maxcols = debug_cols[0];                              /* math.max(table.unpack(cols)) */
+    if (debug_rows == 2 && debug_cols[1] > maxcols) maxcols = debug_cols[1];
+    out->lens_width = maxcols;
+    out->lens_height = debug_rows;
+    return 1;
+}
+
+static int debug_inverse(double x, double y, double o[3], void *ud)
+{ /* row :31-38, col :22-29, lens_inverse :40-57 */
+    if (!ud) return -1;
+    double ny = -y + debug_rows / 2.0; /* rows/2: Lua numbers are doubles */
+    double r, v = modf(ny, &r);
+    if (ny < 0 || ny >= debug_rows) return 0;
+    double rowcols = debug_cols[(int)r];
+    double nx = x + rowcols / 2;
+    double c, u = modf(nx, &c);
+    if (nx < 0 || nx >= rowcols) return 0;
+    double plate = c;
+    for (double i = 0; i < r; i = i + 1) plate = plate + debug_cols[(int)i];
+    return orc_lua_plate_to_ray((const orc_globe *)ud, plate, u, v, o) ? 1 : 0;
+}
+
 /* ---- lenses/polyconic.lua --------------------------------------------------- */
 static int polyconic_forward(double x, double y, double z, double *ox, double *oy, void *ud)
 { /* :7-15 */
@@ -1044,6 +1078,9 @@ int orc_find_lens(const char *name, orc_lens_def *out)
         orc_lua_latlon_to_ray(pi / 2, 0, r);
         gins8_forward(r[0], r[1], r[2], &x, &y, 0);
         out->lens_height = 2 * fabs(y);
+    } else if (!strcmp(name, "debug")) {
+        out->inverse = debug_inverse;   /* + orc_debug_lens(numplates) for the size; ud = the globe */
+        out->onload = "f_contain";
     } else if (!strcmp(name, "cubestereo")) {
         out->inverse = cubestereo_inverse; out->forward = cubestereo_forward;
         out->max_fov = 270; out->max_vfov = 270; out->onload = "f_fov 180";

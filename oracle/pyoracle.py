@@ -183,7 +183,7 @@ FORWARD_CB = ctypes.CFUNCTYPE(c_int, c_double, c_double, c_double, POINTER(c_dou
 TRANSCRIBED_LENSES = ["panini", "stereographic", "rectilinear", "equirect", "cylinder", "mercator", "hammer",
                       "fisheye1", "fisheye2", "quincuncial", "sinusoidal", "winkel1", "mollweide", "vandergrinten", "cube",
                       "winkeltripel", "eckert4", "miller", "gallstereo", "fahey", "eckert1", "eckert5", "kavrayskiy7", "winkel2",
-                      "wagner6", "larrivee", "gins8", "polyconic", "gumby", "cubestereo"]
+                      "wagner6", "larrivee", "gins8", "polyconic", "gumby", "cubestereo", "debug"]
 TRANSCRIBED_GLOBES = ["cube", "trism", "tetra", "cube_edge", "cube_corner", "fast"]
 
 
@@ -221,8 +221,8 @@ class Restatement:
     def lens_inverse(self, lens: str, x: float, y: float):
         """raw result of the C transcription of <lens>.lua's lens_inverse: (status, (rx, ry, rz))"""
         D = _LensDef()
-        if not self.lib.orc_find_lens(lens.encode(), ctypes.byref(D)) or not D.inverse:
-            raise KeyError(lens)
+        if lens == "debug" or not self.lib.orc_find_lens(lens.encode(), ctypes.byref(D)) or not D.inverse:
+            raise KeyError(lens)   # (debug needs a globe: only through build())
         fn = INVERSE_CB(D.inverse)
         out = (c_double * 3)()
         st = fn(x, y, out, None)
@@ -254,6 +254,10 @@ class Restatement:
         D = _LensDef()
         if not L.orc_find_lens(lens.encode(), ctypes.byref(D)):
             raise KeyError(lens)
+        ud = None
+        if lens == "debug":   # sizes itself from numplates, calls plate_to_ray
+            L.orc_debug_lens(G.numplates, ctypes.byref(D))
+            ud = ctypes.byref(G)
         if zoom is None:
             parts = D.onload.decode().split()
             zoom = (parts[0], int(parts[1]) if len(parts) > 1 else 0)
@@ -269,7 +273,7 @@ class Restatement:
         if inverse_cb is not None:
             rc = L.orc_build_inverse(ctypes.byref(G), ctypes.byref(rb), ctypes.byref(LM), inverse_cb, None)
         elif D.inverse:
-            rc = L.orc_build_inverse(ctypes.byref(G), ctypes.byref(rb), ctypes.byref(LM), c_void_p(D.inverse), None)
+            rc = L.orc_build_inverse(ctypes.byref(G), ctypes.byref(rb), ctypes.byref(LM), c_void_p(D.inverse), ud)
         else:
             rc = L.orc_build_forward(ctypes.byref(G), ctypes.byref(rb), ctypes.byref(LM), c_void_p(D.forward), None)
         plates = np.array([list(G.plates[i].forward) + list(G.plates[i].right) + list(G.plates[i].up) +
