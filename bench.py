@@ -317,7 +317,9 @@ def roofline_entry(fe, launch_s, frames, peak, traffic):
            "compulsory_bytes_per_launch": comp, "compulsory_frac": round(comp / launch_s / 1e9 / peak, 4),
            "face_sector_bytes_per_frame": face_sector_bytes}
     if traffic:
-        out["traffic"] = traffic
+        # the contract's `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of this workload's launch (one ncu --set full capture)
+        out["traffic"] = int(traffic["dram_bytes_per_launch"])
+        out["traffic_detail"] = traffic
         out["dram_frac"] = round(traffic["dram_bytes_per_launch"] / launch_s / 1e9 / peak, 4)
     else:
         out["traffic"] = None
