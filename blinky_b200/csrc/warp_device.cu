@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) warp_scalar_kernel(const WarpParams 
 // self-feeding version spent 36 of 213 instructions per frame copying registers that an
 // uninitialised array in the GATHER path kept live around the unit loop, and the GATHER path's 130
 // registers capped the kernel at 160 registers per thread.  Now the frame loop is ~140
-// instructions at 96 registers.  What is left is not one bottleneck: with the 4K panini batch at
+// instructions at 100 registers.  What is left is not one bottleneck: with the 4K panini batch at
 // 4.4 us per frame (ring warps alone), removing the stores gives 3.2, removing the box loads 3.4,
 // both 2.6, conflict-free shared loads 4.4, 128-byte instead of 32-byte store segments 4.3 — DRAM
 // time (2.7 us for the 17.5 MB a frame moves) and issue time overlap only partly with 12 warps,
@@ -751,8 +751,8 @@ __global__ void __launch_bounds__(32, MINB) warp_ring_kernel(const __grid_consta
 // K3: the GATHER tiles of plans in which they are many (more than kMergedGatherPercent of the tiles:
 // minifying lenses, where a tile's texels do not fit a box), launched in front of the ring kernel; with
 // few GATHER tiles they ride in the ring kernel's launch instead (gather_item).  Those tiles are bound
-// by global-load latency and, at 32-byte sectors scattered over DRAM pages, by DRAM itself (ncu: 47 %
-// of DRAM peak with one useful byte in 18 fetched); they get plain parallelism: grid = (tiles, groups of 4 frames), 256 threads, a warp owns 4 tile rows and lane l is
+// by global-load latency and, at 32-byte sectors scattered over DRAM pages, by DRAM itself (ncu, 4K fisheye1:
+// 4.6 TB/s = 70 % of the measured copy peak with about one useful byte in 20 fetched); they get plain parallelism: grid = (tiles, groups of 4 frames), 256 threads, a warp owns 4 tile rows and lane l is
 // column l (one warp-level load = 32 consecutive screen pixels of one row).  The tile's entries are
 // fetched once and reused for the frames of the group; all 16 gathers of a thread are issued before
 // its first store.
@@ -1140,7 +1140,7 @@ WarpDevice::TmapSet *WarpDevice::get_tmaps(const void *d_faces, size_t face_stri
 }
 
 // CTAs per SM the ring kernel's register allocation is sized for: 16 (128 registers per thread; the BOX path uses 96,
-// 118 with the rubix overlay).  How many ring warps are resident is decided in launch_ring.
+// 116 with the rubix overlay).  How many ring warps are resident is decided in launch_ring.
 template <bool RUBIX>
 constexpr int ring_warps() { return 16; }
 // Resident ring warps per SM by default (BLINKY_RING_CTAS): measured on the 4K panini batch 12 / 14 / 16 warps give
