@@ -219,6 +219,7 @@ private:
         for (const Block *b : s->blocks) scan_block(fn, b, seen);
         if (s->k == SK::GenFor) fail("generic 'for ... in' is not supported", s->line);
         if (s->k == SK::LocalFunction) fail("local functions inside the lens are not supported", s->line);
+        if (s->k == SK::Goto || s->k == SK::Label) fail("goto is not supported", s->line);
     }
 
     // ------------------------------------------------------------------ per-function generation state
@@ -943,6 +944,8 @@ private:
             case SK::Break: line(g, "break;"); return;
             case SK::GenFor: fail("generic 'for ... in' is not supported", s->line);
             case SK::LocalFunction: fail("local functions inside the lens are not supported", s->line);
+            case SK::Goto:
+            case SK::Label: fail("goto is not supported", s->line);
         }
     }
 

@@ -843,8 +843,19 @@ private:
                 if (fs_->loop_depth == 0) lex_.error("<break> at line " + std::to_string(line) + " not inside a loop", line);
                 return new_stmt(SK::Break, line);
             }
-            case T_GOTO: err("'goto' is not supported by this evaluator");
-            case T_DBCOLON: err("labels are not supported by this evaluator");
+            case T_GOTO: {   // Lua 5.2 (the reference links liblua 5.2): resolved when executed, see exec_block
+                advance();
+                Stmt *s = new_stmt(SK::Goto, line);
+                s->label = expect_name();
+                return s;
+            }
+            case T_DBCOLON: {
+                advance();
+                Stmt *s = new_stmt(SK::Label, line);
+                s->label = expect_name();
+                if (!accept(T_DBCOLON)) err("'::' expected");
+                return s;
+            }
             default: return parse_expr_stat();
         }
     }
@@ -1216,9 +1227,12 @@ struct Frame {
     const Value *varargs;
     int nvarargs;
     const Chunk *chunk;
+    const Stmt *pending_goto = nullptr;   // the `goto` being unwound (Flow::Goto)
 };
 
-enum class Flow { Normal, Break, Return };
+// Goto: a `goto` looking for its label — every enclosing block is searched on the way out (a label is visible in the
+// block that holds it and the blocks nested in it, which is where Lua 5.2 lets a goto sit); loops and ifs pass it on
+enum class Flow { Normal, Break, Return, Goto };
 
 [[noreturn]] void rt_error(const Frame &f, int line, const std::string &msg) {
     std::ostringstream o;
@@ -1712,6 +1726,10 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
             eval_call(L, f, s->e, rets);
             return Flow::Normal;
         }
+        case SK::Goto:
+            f.pending_goto = s;
+            return Flow::Goto;
+        case SK::Label: return Flow::Normal;
         case SK::Do: return exec_block(L, f, s->body, ret);
         case SK::While: {
             for (;;) {
@@ -1720,7 +1738,7 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
                 if (!c.truthy()) break;
                 Flow fl = exec_block(L, f, s->body, ret);
                 if (fl == Flow::Break) break;
-                if (fl == Flow::Return) return fl;
+                if (fl == Flow::Return || fl == Flow::Goto) return fl;
             }
             return Flow::Normal;
         }
@@ -1728,7 +1746,7 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
             for (;;) {
                 Flow fl = exec_block(L, f, s->body, ret);
                 if (fl == Flow::Break) break;
-                if (fl == Flow::Return) return fl;
+                if (fl == Flow::Return || fl == Flow::Goto) return fl;
                 Value c;
                 eval(L, f, s->e, c);
                 if (c.truthy()) break;
@@ -1763,7 +1781,7 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
                 declare_slot(L, f, s->vars[0], Value(idx));
                 Flow fl = exec_block(L, f, s->body, ret);
                 if (fl == Flow::Break) break;
-                if (fl == Flow::Return) return fl;
+                if (fl == Flow::Return || fl == Flow::Goto) return fl;
             }
             return Flow::Normal;
         }
@@ -1785,7 +1803,7 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
                     declare_slot(L, f, s->vars[i], static_cast<int>(i) < rets.size() ? rets[static_cast<int>(i)] : Value());
                 Flow fl = exec_block(L, f, s->body, ret);
                 if (fl == Flow::Break) break;
-                if (fl == Flow::Return) return fl;
+                if (fl == Flow::Return || fl == Flow::Goto) return fl;
             }
             return Flow::Normal;
         }
@@ -1806,8 +1824,18 @@ Flow exec_stmt(State &L, Frame &f, const Stmt *s, ValueList &ret) {
 }
 
 Flow exec_block(State &L, Frame &f, const Block *b, ValueList &ret) {
-    for (const Stmt *s : b->stmts) {
-        Flow fl = exec_stmt(L, f, s, ret);
+    for (size_t i = 0; i < b->stmts.size(); ++i) {
+        Flow fl = exec_stmt(L, f, b->stmts[i], ret);
+        if (fl == Flow::Goto) {
+            // is the label in this block?  then execution continues behind it (backward jumps included)
+            size_t at = b->stmts.size();
+            for (size_t k = 0; k < b->stmts.size(); ++k)
+                if (b->stmts[k]->k == SK::Label && b->stmts[k]->label == f.pending_goto->label) at = k;
+            if (at == b->stmts.size()) return fl;   // not here: an enclosing block's
+            f.pending_goto = nullptr;
+            i = at;                                  // (the loop's ++i steps over the label itself)
+            continue;
+        }
         if (fl != Flow::Normal) return fl;
     }
     return Flow::Normal;
@@ -1863,7 +1891,7 @@ void call_value(State &L, const Value &fnv, const Value *args, int nargs, ValueL
         f.varargs = nullptr;
         f.nvarargs = 0;
     }
-    exec_block(L, f, p->body, out);
+    if (exec_block(L, f, p->body, out) == Flow::Goto) rt_error(f, f.pending_goto->line, "no visible label '" + f.pending_goto->label + "' for goto");
 }
 
 }  // namespace

@@ -43,6 +43,7 @@ struct Expr {
 
 enum class SK : uint8_t {
     Local, Assign, Call, Do, While, Repeat, If, NumFor, GenFor, Return, Break, LocalFunction,
+    Goto, Label,   // Lua 5.2 `goto name` / `::name::` (Stmt::label)
 };
 
 struct Block;
@@ -57,6 +58,7 @@ struct Stmt {
     Block *body = nullptr;         // Do / While / Repeat / NumFor / GenFor
     std::vector<Expr *> conds;     // If
     std::vector<Block *> blocks;   // If (conds.size() or conds.size()+1 entries)
+    std::string label;             // Goto / Label
 };
 
 struct Block {

@@ -97,6 +97,61 @@ assert(cnt == 3)
 """)
 
 
+def test_goto_and_labels(lua):
+    """Lua 5.2 goto (the reference links liblua 5.2, so user lenses may use it): the continue idiom, backward
+    jumps, jumping out of nested loops and blocks, labels at the end of repeat bodies, and a goto without label"""
+    ok(lua, """
+local s = 0
+for i = 1, 10 do
+  if i % 2 == 0 then goto continue end
+  s = s + i
+  ::continue::
+end
+assert(s == 25)
+local n = 0
+::top::
+n = n + 1
+if n < 5 then goto top end
+assert(n == 5)
+local hit
+for i = 1, 3 do
+  for j = 1, 3 do
+    if i * j == 4 then hit = i * 10 + j goto out end
+  end
+end
+::out::
+assert(hit == 22)
+local function f(x)
+  do
+    if x > 1 then goto big end
+    return "small"
+  end
+  ::big::
+  return "big"
+end
+assert(f(0) == "small" and f(5) == "big")
+local k, skipped = 0, 0
+repeat
+  k = k + 1
+  if k == 2 then goto skip end
+  skipped = skipped + 1
+  ::skip::
+until k >= 3
+assert(k == 3 and skipped == 2)
+local i = 0
+while true do
+  i = i + 1
+  if i > 3 then goto done end
+end
+::done::
+assert(i == 4)
+local okc, err = pcall(function() goto nowhere end)
+assert(not okc and type(err) == "string")
+""")
+    rc, out, err = lua("goto nowhere")
+    assert rc != 0 and "no visible label 'nowhere'" in err
+
+
 def test_arithmetic_follows_ieee_and_lua(lua):
     ok(lua, """
 assert(2^10 == 1024 and 7 % 3 == 1 and -7 % 3 == 2 and 7 % -3 == -2)
