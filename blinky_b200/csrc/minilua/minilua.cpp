@@ -2323,6 +2323,319 @@ void s_char(State &L, const Value *a, int n, ValueList &out, void *) {
     for (int i = 1; i <= n; ++i) s.push_back(static_cast<char>(static_cast<int>(check_number(a, n, i, "char"))));
     out.push_back(L.new_string(s));
 }
+// ---- Lua patterns (reference manual 6.4.1): character classes %a %c %d %g %l %p %s %u %w %x and their
+// complements, sets [...], the quantifiers * + - ?, anchors ^ $, captures ( ) and position captures (),
+// back-references %1-%9, %bxy and the frontier %f[set].  A backtracking matcher over byte strings.
+struct PatMatch {
+    const char *src, *src_end, *pat_end;
+    int level = 0, depth = 0;
+    struct { const char *init; long len; } cap[32];
+    static constexpr long kUnfinished = -1, kPosition = -2;
+
+    [[noreturn]] static void bad(const char *m) { throw LuaError(m); }
+
+    static bool in_class(int c, int cl) {
+        bool r;
+        switch (tolower(cl)) {
+            case 'a': r = isalpha(c); break;
+            case 'c': r = iscntrl(c); break;
+            case 'd': r = isdigit(c); break;
+            case 'g': r = isgraph(c); break;
+            case 'l': r = islower(c); break;
+            case 'p': r = ispunct(c); break;
+            case 's': r = isspace(c); break;
+            case 'u': r = isupper(c); break;
+            case 'w': r = isalnum(c); break;
+            case 'x': r = isxdigit(c); break;
+            default: return cl == c;
+        }
+        return isupper(cl) ? !r : r;
+    }
+    // end of the single-character item that starts at p
+    const char *item_end(const char *p) const {
+        if (p == pat_end) bad("malformed pattern (ends with '%')");
+        const unsigned char c = static_cast<unsigned char>(*p++);
+        if (c == '%') {
+            if (p == pat_end) bad("malformed pattern (ends with '%')");
+            return p + 1;
+        }
+        if (c == '[') {
+            if (p < pat_end && *p == '^') ++p;
+            do {   // the first character may be ']'
+                if (p == pat_end) bad("malformed pattern (missing ']')");
+                if (*p++ == '%' && p < pat_end) ++p;
+            } while (p == pat_end || *p != ']');
+            return p + 1;
+        }
+        return p;
+    }
+    bool in_set(int c, const char *p, const char *set_end) const {   // p at '[', set_end at ']'
+        bool neg = false;
+        if (p[1] == '^') { neg = true; ++p; }
+        while (++p < set_end) {
+            if (*p == '%') {
+                ++p;
+                if (in_class(c, static_cast<unsigned char>(*p))) return !neg;
+            } else if (p[1] == '-' && p + 2 < set_end) {
+                if (static_cast<unsigned char>(p[0]) <= c && c <= static_cast<unsigned char>(p[2])) return !neg;
+                p += 2;
+            } else if (static_cast<unsigned char>(*p) == c) {
+                return !neg;
+            }
+        }
+        return neg;
+    }
+    bool single(const char *s, const char *p, const char *ep) const {
+        if (s >= src_end) return false;
+        const int c = static_cast<unsigned char>(*s);
+        switch (*p) {
+            case '.': return true;
+            case '%': return in_class(c, static_cast<unsigned char>(p[1]));
+            case '[': return in_set(c, p, ep - 1);
+            default: return static_cast<unsigned char>(*p) == c;
+        }
+    }
+    const char *match(const char *s, const char *p) {
+        if (++depth > 200) bad("pattern too complex");
+        const char *r = do_match(s, p);
+        --depth;
+        return r;
+    }
+    const char *do_match(const char *s, const char *p) {
+        for (;;) {
+            if (p == pat_end) return s;
+            switch (*p) {
+                case '(':
+                    if (p + 1 < pat_end && p[1] == ')') return open_capture(s, p + 2, kPosition);
+                    return open_capture(s, p + 1, kUnfinished);
+                case ')': return close_capture(s, p + 1);
+                case '$':
+                    if (p + 1 == pat_end) return s == src_end ? s : nullptr;
+                    break;
+                case '%':
+                    if (p + 1 < pat_end && p[1] == 'b') return balance(s, p + 2);
+                    if (p + 1 < pat_end && p[1] == 'f') {
+                        p += 2;
+                        if (p == pat_end || *p != '[') bad("missing '[' after '%f' in pattern");
+                        const char *ep = item_end(p);
+                        const int prev = s == src ? 0 : static_cast<unsigned char>(s[-1]);
+                        const int cur = s < src_end ? static_cast<unsigned char>(*s) : 0;
+                        if (!in_set(prev, p, ep - 1) && in_set(cur, p, ep - 1)) { p = ep; continue; }
+                        return nullptr;
+                    }
+                    if (p + 1 < pat_end && isdigit(static_cast<unsigned char>(p[1]))) {
+                        const int l = p[1] - '1';
+                        if (l < 0 || l >= level || cap[l].len == kUnfinished) bad("invalid capture index in pattern");
+                        const size_t len = static_cast<size_t>(cap[l].len);
+                        if (static_cast<size_t>(src_end - s) >= len && memcmp(cap[l].init, s, len) == 0) { s += len; p += 2; continue; }
+                        return nullptr;
+                    }
+                    break;
+                default: break;
+            }
+            const char *ep = item_end(p);
+            const char q = ep < pat_end ? *ep : '\0';
+            if (q == '?') {
+                if (single(s, p, ep)) {
+                    if (const char *r = match(s + 1, ep + 1)) return r;
+                }
+                p = ep + 1;
+                continue;
+            }
+            if (q == '+') return single(s, p, ep) ? max_expand(s + 1, p, ep) : nullptr;
+            if (q == '*') return max_expand(s, p, ep);
+            if (q == '-') {
+                for (;;) {
+                    if (const char *r = match(s, ep + 1)) return r;
+                    if (single(s, p, ep)) ++s; else return nullptr;
+                }
+            }
+            if (!single(s, p, ep)) return nullptr;
+            ++s;
+            p = ep;
+        }
+    }
+    const char *max_expand(const char *s, const char *p, const char *ep) {
+        long i = 0;
+        while (single(s + i, p, ep)) ++i;
+        for (; i >= 0; --i)
+            if (const char *r = match(s + i, ep + 1)) return r;
+        return nullptr;
+    }
+    const char *open_capture(const char *s, const char *p, long what) {
+        if (level >= 32) bad("too many captures");
+        cap[level].init = s;
+        cap[level].len = what;
+        ++level;
+        const char *r = match(s, p);
+        if (!r) --level;
+        return r;
+    }
+    const char *close_capture(const char *s, const char *p) {
+        int l = level - 1;
+        while (l >= 0 && cap[l].len != kUnfinished) --l;
+        if (l < 0) bad("invalid pattern capture");
+        cap[l].len = s - cap[l].init;
+        const char *r = match(s, p);
+        if (!r) cap[l].len = kUnfinished;
+        return r;
+    }
+    const char *balance(const char *s, const char *p) {
+        if (p + 1 >= pat_end) bad("malformed pattern (missing arguments to '%b')");
+        if (s >= src_end || *s != *p) return nullptr;
+        const int open = *p, close = p[1];
+        int cont = 1;
+        for (const char *t = s + 1; t < src_end; ++t) {
+            if (*t == close) {
+                if (--cont == 0) return match(t + 1, p + 2);
+            } else if (*t == open) {
+                ++cont;
+            }
+        }
+        return nullptr;
+    }
+    void push_capture(State &L, int i, const char *s, const char *e, ValueList &out) const {
+        if (i >= level) {
+            if (i == 0) out.push_back(L.new_string(std::string(s, e)));   // no explicit captures: the whole match
+            else bad("invalid capture index");
+            return;
+        }
+        if (cap[i].len == kUnfinished) bad("unfinished capture");
+        if (cap[i].len == kPosition) out.push_back(Value(static_cast<double>(cap[i].init - src + 1)));
+        else out.push_back(L.new_string(std::string(cap[i].init, static_cast<size_t>(cap[i].len))));
+    }
+};
+
+// string.find / string.match
+void str_find_aux(State &L, const Value *a, int n, ValueList &out, bool find, const char *fname) {
+    const std::string s = check_string(a, n, 1, fname), pat = check_string(a, n, 2, fname);
+    long init = static_cast<long>(opt_number(a, n, 3, fname, 1));
+    const long ls = static_cast<long>(s.size());
+    if (init < 0) init = std::max(ls + init + 1, 1L); else if (init == 0) init = 1;
+    if (init > ls + 1) { out.push_back(Value()); return; }
+    const bool plain = find && n >= 4 && a[3].truthy();
+    if (find && (plain || pat.find_first_of("^$*+?.([%-") == std::string::npos)) {
+        const size_t at = s.find(pat, static_cast<size_t>(init - 1));
+        if (at == std::string::npos) { out.push_back(Value()); return; }
+        out.push_back(Value(static_cast<double>(at + 1)));
+        out.push_back(Value(static_cast<double>(at + pat.size())));
+        return;
+    }
+    PatMatch m;
+    m.src = s.data();
+    m.src_end = s.data() + s.size();
+    const char *p = pat.data();
+    m.pat_end = pat.data() + pat.size();
+    const bool anchor = !pat.empty() && *p == '^';
+    if (anchor) ++p;
+    const char *s1 = s.data() + init - 1;
+    do {
+        m.level = 0;
+        m.depth = 0;
+        if (const char *e = m.match(s1, p)) {
+            if (find) {
+                out.push_back(Value(static_cast<double>(s1 - s.data() + 1)));
+                out.push_back(Value(static_cast<double>(e - s.data())));
+                for (int i = 0; i < m.level; ++i) m.push_capture(L, i, s1, e, out);
+            } else {
+                const int nc = m.level == 0 ? 1 : m.level;
+                for (int i = 0; i < nc; ++i) m.push_capture(L, i, s1, e, out);
+            }
+            return;
+        }
+    } while (s1++ < m.src_end && !anchor);
+    out.push_back(Value());
+}
+void s_find(State &L, const Value *a, int n, ValueList &out, void *) { str_find_aux(L, a, n, out, true, "find"); }
+void s_match(State &L, const Value *a, int n, ValueList &out, void *) { str_find_aux(L, a, n, out, false, "match"); }
+void s_reverse(State &L, const Value *a, int n, ValueList &out, void *) {
+    std::string s = check_string(a, n, 1, "reverse");
+    std::reverse(s.begin(), s.end());
+    out.push_back(L.new_string(s));
+}
+
+// string.gmatch and string.gsub sit on string.find in Lua itself (run once per State)
+const char *kStringPrelude = R"LUA(
+function string.gmatch(s, p)
+  local pos, done = 1, false
+  return function()
+    if done then return nil end
+    local r = table.pack(string.find(s, p, pos))
+    local st, e = r[1], r[2]
+    if st == nil then done = true return nil end
+    if e >= st then pos = e + 1 else pos = st + 1 end
+    if pos > #s + 1 then done = true end
+    if r.n > 2 then return table.unpack(r, 3, r.n) end
+    return string.sub(s, st, e)
+  end
+end
+function string.gsub(s, p, repl, max_n)
+  local tr = type(repl)
+  if tr ~= "string" and tr ~= "number" and tr ~= "table" and tr ~= "function" then
+    error("bad argument #3 to 'gsub' (string/function/table expected)")
+  end
+  local out, pos, count, anchor = {}, 1, 0, string.sub(p, 1, 1) == "^"
+  while max_n == nil or count < max_n do
+    local r = table.pack(string.find(s, p, pos))
+    local st, e = r[1], r[2]
+    if st == nil then break end
+    count = count + 1
+    out[#out + 1] = string.sub(s, pos, st - 1)
+    local whole = string.sub(s, st, e)
+    local rv
+    if tr == "string" or tr == "number" then
+      local rs, acc, i = tostring(repl), {}, 1
+      while i <= #rs do
+        local c = string.sub(rs, i, i)
+        if c ~= "%" then
+          acc[#acc + 1] = c
+        else
+          i = i + 1
+          local d = string.sub(rs, i, i)
+          if d == "%" then
+            acc[#acc + 1] = "%"
+          elseif d == "0" then
+            acc[#acc + 1] = whole
+          elseif d >= "1" and d <= "9" and #d == 1 then
+            local k = tonumber(d)
+            if k == 1 and r.n == 2 then
+              acc[#acc + 1] = whole
+            elseif k + 2 > r.n then
+              error("invalid capture index %" .. d .. " in replacement string")
+            else
+              acc[#acc + 1] = tostring(r[k + 2])
+            end
+          else
+            error("invalid use of '%' in replacement string")
+          end
+        end
+        i = i + 1
+      end
+      rv = table.concat(acc)
+    elseif tr == "table" then
+      if r.n > 2 then rv = repl[r[3]] else rv = repl[whole] end
+    else
+      if r.n > 2 then rv = repl(table.unpack(r, 3, r.n)) else rv = repl(whole) end
+    end
+    if rv == nil or rv == false then
+      rv = whole
+    elseif type(rv) ~= "string" and type(rv) ~= "number" then
+      error("invalid replacement value (a " .. type(rv) .. ")")
+    end
+    out[#out + 1] = tostring(rv)
+    if e >= st then
+      pos = e + 1
+    else
+      out[#out + 1] = string.sub(s, st, st)
+      pos = st + 1
+    end
+    if pos > #s + 1 or anchor then break end
+  end
+  out[#out + 1] = string.sub(s, pos)
+  return table.concat(out), count
+end
+)LUA";
+
 void s_format(State &L, const Value *a, int n, ValueList &out, void *) {
     std::string fmt = check_string(a, n, 1, "format");
     std::string r;
@@ -2754,7 +3067,11 @@ void State::open_libs() {
     reg(*this, s, "byte", s_byte);
     reg(*this, s, "char", s_char);
     reg(*this, s, "format", s_format);
+    reg(*this, s, "find", s_find);
+    reg(*this, s, "match", s_match);
+    reg(*this, s, "reverse", s_reverse);
     set_global("string", sv);
+    run(kStringPrelude, "=string");
 }
 
 // ---------------------------------------------------------------------------

@@ -224,6 +224,44 @@ assert(tonumber("12") == 12 and tonumber("z") == nil and tonumber("ff", 16) == 2
 """)
 
 
+def test_string_patterns(lua):
+    """string.find / match / gmatch / gsub / reverse with Lua patterns (reference manual 6.4.1)"""
+    ok(lua, """
+assert(select('#', string.find("hello world", "o w")) == 2)
+local a, b = string.find("hello world", "o w") assert(a == 5 and b == 7)
+a, b = string.find("hello world", "l+") assert(a == 3 and b == 4)
+assert(string.find("hello", "xyz") == nil)
+a, b = string.find("a.b", ".", 1, true) assert(a == 2 and b == 2)
+local s, e, k, v = string.find("key = value", "(%w+)%s*=%s*(%w+)") assert(s == 1 and e == 11 and k == "key" and v == "value")
+local y, m, d = string.match("2024-09-23", "(%d+)-(%d+)-(%d+)") assert(y == "2024" and m == "09" and d == "23")
+assert(string.match("  trim  ", "^%s*(.-)%s*$") == "trim")
+local p1, p2 = string.match("hello", "()ll()") assert(p1 == 3 and p2 == 5)
+assert(string.match("THE (quick) fox", "%((%a+)%)") == "quick")
+assert(string.match("f(a(b)c)d", "%b()") == "(a(b)c)")
+assert(string.match("THE END", "%f[%a]%a+", 5) == "END")
+assert(string.match("0x1F", "^0[xX](%x+)$") == "1F")
+assert(string.match("aaa", "a-b") == nil and string.match("aaab", "a-b") == "aaab")
+assert(string.match("x=1;x=1", "(x=%d);%1") == "x=1")
+local r, n = string.gsub("hello world", "o", "0") assert(r == "hell0 w0rld" and n == 2)
+r, n = string.gsub("hello world", "(%w+)", "<%1>") assert(r == "<hello> <world>" and n == 2)
+r, n = string.gsub("abc", "", "-") assert(r == "-a-b-c-" and n == 4)
+r, n = string.gsub("hello", "l", {l = "L"}) assert(r == "heLLo" and n == 2)
+r, n = string.gsub("1 2 3", "%d", function(d) return d * 2 end, 2) assert(r == "2 4 3" and n == 2)
+r, n = string.gsub("abc", "^a", "X") assert(r == "Xbc" and n == 1)
+r, n = string.gsub("x = $y", "%$(%w+)", "%%%1") assert(r == "x = %y" and n == 1)
+r, n = string.gsub("abc", "%w", "%0%0") assert(r == "aabbcc" and n == 3)
+local t = {}
+for k, v in string.gmatch("a=1, b=2", "(%w+)=(%w+)") do t[#t + 1] = k .. v end
+assert(table.concat(t, ",") == "a1,b2")
+t = {}
+for w in string.gmatch("one two", "%a+") do t[#t + 1] = w end
+assert(#t == 2 and t[2] == "two")
+assert(("abc"):reverse() == "cba" and ("abc"):find("c") == 3)
+assert(not pcall(string.find, "a", "[a"))
+assert(not pcall(string.gsub, "a", "a", "%2"))
+""")
+
+
 def test_errors_are_caught_and_positioned(lua):
     out = ok(lua, """
 local ok, err = pcall(function() local z = nil; return z + 1 end)
