@@ -12,6 +12,7 @@
 #include <cinttypes>
 #include <algorithm>
 #include <cmath>
+#include <ctime>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -2169,6 +2170,60 @@ void b_pcall(State &L, const Value *a, int n, ValueList &out, void *) {
         out.push_back(L.new_string(e.what()));
     }
 }
+void b_xpcall(State &L, const Value *a, int n, ValueList &out, void *) {
+    if (n < 2) arg_error(2, "xpcall", "value expected");
+    ValueList rets;
+    int saved_depth = L.depth;
+    try {
+        L.call(a[0], a + 2, n - 2, rets);
+        out.push_back(Value::boolean(true));
+        for (int i = 0; i < rets.size(); ++i) out.push_back(rets[i]);
+    } catch (LuaError &e) {
+        L.depth = saved_depth;
+        Value msg = L.new_string(e.what());
+        ValueList h;
+        L.call(a[1], &msg, 1, h);   // the message handler's results replace the message
+        out.push_back(Value::boolean(false));
+        for (int i = 0; i < h.size(); ++i) out.push_back(h[i]);
+    }
+}
+void b_collectgarbage(State &, const Value *a, int n, ValueList &out, void *) {
+    // memory is reference counted (plus cycle collection at State teardown): nothing to do, report 0 KB
+    const std::string opt = (n >= 1 && a[0].is_string()) ? a[0].str() : std::string("collect");
+    if (opt == "isrunning") out.push_back(Value::boolean(true));
+    else out.push_back(Value(0.0));
+}
+void b_load(State &L, const Value *a, int n, ValueList &out, void *) {
+    // load(string [, chunkname]): compiled in the current State's global environment
+    if (n < 1 || !a[0].is_string()) arg_error(1, "load", "string expected (functions as chunk readers are not supported)");
+    const std::string name = (n >= 2 && a[1].is_string()) ? a[1].str() : "=(load)";
+    try {
+        out.push_back(L.load(a[0].str(), name));
+    } catch (LuaError &e) {
+        out.push_back(Value());
+        out.push_back(L.new_string(e.what()));
+    }
+}
+void os_time(State &, const Value *, int, ValueList &out, void *) { out.push_back(Value(static_cast<double>(time(nullptr)))); }
+void os_clock(State &, const Value *, int, ValueList &out, void *) { out.push_back(Value(static_cast<double>(clock()) / CLOCKS_PER_SEC)); }
+void os_getenv(State &L, const Value *a, int n, ValueList &out, void *) {
+    const char *v = getenv(check_string(a, n, 1, "getenv").c_str());
+    out.push_back(v ? L.new_string(v) : Value());
+}
+void os_date(State &L, const Value *a, int n, ValueList &out, void *) {
+    std::string fmt = n >= 1 && a[0].is_string() ? a[0].str() : "%c";
+    time_t t = n >= 2 ? static_cast<time_t>(check_number(a, n, 2, "date")) : time(nullptr);
+    struct tm tmv;
+    if (!fmt.empty() && fmt[0] == '!') { gmtime_r(&t, &tmv); fmt.erase(0, 1); } else localtime_r(&t, &tmv);
+    char buf[256];
+    out.push_back(L.new_string(std::string(buf, strftime(buf, sizeof buf, fmt.c_str(), &tmv))));
+}
+void io_write(State &L, const Value *a, int n, ValueList &, void *) {
+    // goes where print() goes, without separators or the newline
+    std::string s;
+    for (int i = 1; i <= n; ++i) s += check_string(a, n, i, "write");
+    L.emit_print(s);
+}
 void b_rawequal(State &, const Value *a, int n, ValueList &out, void *) {
     out.push_back(Value::boolean(n >= 2 && a[0].raw_equals(a[1])));
 }
@@ -3004,6 +3059,10 @@ void State::open_libs() {
     register_function("pairs", b_pairs);
     register_function("ipairs", b_ipairs);
     register_function("pcall", b_pcall);
+    register_function("xpcall", b_xpcall);
+    register_function("collectgarbage", b_collectgarbage);
+    register_function("load", b_load);
+    register_function("loadstring", b_load);  // 5.1 name
     register_function("rawequal", b_rawequal);
     register_function("rawlen", b_rawlen);
     register_function("rawget", b_rawget);
@@ -3071,6 +3130,18 @@ void State::open_libs() {
     reg(*this, s, "match", s_match);
     reg(*this, s, "reverse", s_reverse);
     set_global("string", sv);
+
+    // the corners of os / io a lens script might touch (clock for timing prints, write for progress dots); no file access
+    Value ov = new_table();
+    Table *o = static_cast<Table *>(ov.obj());
+    reg(*this, o, "time", os_time);
+    reg(*this, o, "clock", os_clock);
+    reg(*this, o, "date", os_date);
+    reg(*this, o, "getenv", os_getenv);
+    set_global("os", ov);
+    Value iv = new_table();
+    reg(*this, static_cast<Table *>(iv.obj()), "write", io_write);
+    set_global("io", iv);
     run(kStringPrelude, "=string");
 }
 

@@ -262,6 +262,27 @@ assert(not pcall(string.gsub, "a", "a", "%2"))
 """)
 
 
+def test_base_library_corners(lua):
+    """xpcall, load, collectgarbage and the harmless corners of os / io (the reference opens all libraries,
+    fisheye.c:1228; file access stays out)"""
+    out = ok(lua, """
+local okc, m = xpcall(function() error("x") end, function(msg) return "handled: " .. msg end)
+assert(okc == false and m:find("handled: ", 1, true) == 1 and m:find("x", 1, true))
+local ok2, v = xpcall(function(a, b) return a + b end, print, 1, 2)
+assert(ok2 == true and v == 3)
+assert(collectgarbage("count") == 0 and collectgarbage() == 0)
+local f = load("return 1 + 2")
+assert(f() == 3)
+local g, err = load("syntax error here")
+assert(g == nil and type(err) == "string")
+assert(type(os.time()) == "number" and type(os.clock()) == "number" and os.date("!%Y", 0) == "1970")
+assert(os.getenv("BLINKY_NO_SUCH_VARIABLE") == nil)
+assert(io.open == nil and os.remove == nil and os.execute == nil)
+io.write("a", 1, "b")
+""")
+    assert out == "a1b"
+
+
 def test_errors_are_caught_and_positioned(lua):
     out = ok(lua, """
 local ok, err = pcall(function() local z = nil; return z + 1 end)
