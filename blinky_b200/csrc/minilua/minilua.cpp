@@ -1287,17 +1287,44 @@ std::string number_to_string(double d) {
     return b;
 }
 
-bool less_than(const Frame &f, int line, const Value &a, const Value &b) {
+// ---- metatables: only tables carry one; every use sits on a path that would otherwise raise an error or
+// return nil, so programs without metatables (all shipped lenses) run exactly as before
+Value metamethod(const Value &v, const char *name) {
+    if (!v.is_table()) return Value();
+    const Value &m = static_cast<const Table *>(v.obj())->meta;
+    if (!m.is_table()) return Value();
+    return static_cast<const Table *>(m.obj())->get_str(name);
+}
+// the handler of a binary event: the left operand's, else the right one's
+Value binary_handler(const Value &a, const Value &b, const char *name) {
+    Value h = metamethod(a, name);
+    return h.is_nil() ? metamethod(b, name) : h;
+}
+bool call_binary(State &L, const Frame &f, int line, const Value &h, const Value &a, const Value &b, Value &out) {
+    if (h.is_nil()) return false;
+    const Value args[2] = {a, b};
+    ValueList rets;
+    call_value(L, h, args, 2, rets, &f, line);
+    out = rets.size() > 0 ? rets[0] : Value();
+    return true;
+}
+
+bool less_than(State &L, const Frame &f, int line, const Value &a, const Value &b) {
     if (a.is_number() && b.is_number()) return a.num() < b.num();
     if (a.is_string() && b.is_string()) return a.str() < b.str();
+    Value r;
+    if (call_binary(L, f, line, binary_handler(a, b, "__lt"), a, b, r)) return r.truthy();
     if (a.type() == b.type())
         rt_error(f, line, std::string("attempt to compare two ") + State::type_name(a) + " values");
     rt_error(f, line, std::string("attempt to compare ") + State::type_name(a) + " with " + State::type_name(b));
 }
 
-bool less_equal(const Frame &f, int line, const Value &a, const Value &b) {
+bool less_equal(State &L, const Frame &f, int line, const Value &a, const Value &b) {
     if (a.is_number() && b.is_number()) return a.num() <= b.num();
     if (a.is_string() && b.is_string()) return a.str() <= b.str();
+    Value r;
+    if (call_binary(L, f, line, binary_handler(a, b, "__le"), a, b, r)) return r.truthy();
+    if (call_binary(L, f, line, binary_handler(b, a, "__lt"), b, a, r)) return !r.truthy();   // a <= b  ==  not (b < a)
     if (a.type() == b.type())
         rt_error(f, line, std::string("attempt to compare two ") + State::type_name(a) + " values");
     rt_error(f, line, std::string("attempt to compare ") + State::type_name(a) + " with " + State::type_name(b));
@@ -1317,8 +1344,27 @@ std::string describe(const Expr *e, const Frame &f) {
 
 void index_value(State &L, Frame &f, const Expr *e, const Value &obj, const Value &key, Value &out) {
     if (obj.is_table()) {
-        out = static_cast<Table *>(obj.obj())->get(key);
-        return;
+        const Table *t = static_cast<Table *>(obj.obj());
+        out = t->get(key);
+        if (!out.is_nil() || !t->meta.is_table()) return;
+        // __index: a table to look in next (chains), or a function(table, key)
+        Value cur = obj;
+        for (int hops = 0; hops < 100; ++hops) {
+            Value h = metamethod(cur, "__index");
+            if (h.is_nil()) return;
+            if (h.is_function()) {
+                const Value args[2] = {cur, key};
+                ValueList rets;
+                call_value(L, h, args, 2, rets, &f, e->line);
+                out = rets.size() > 0 ? rets[0] : Value();
+                return;
+            }
+            if (!h.is_table()) rt_error(f, e->line, std::string("attempt to index a ") + State::type_name(h) + " value");
+            out = static_cast<Table *>(h.obj())->get(key);
+            if (!out.is_nil()) return;
+            cur = h;
+        }
+        rt_error(f, e->line, "loop in gettable");
     }
     if (obj.is_string()) {  // ("x"):len() style access goes through the string library
         Value lib = L.get_global("string");
@@ -1396,6 +1442,13 @@ void eval_call(State &L, Frame &f, const Expr *e, ValueList &out) {
         eval(L, f, e->l, fn);
     }
     eval_args(L, f, e->list, args);
+    if (!fn.is_function() && !metamethod(fn, "__call").is_nil()) {   // callable table: handler(table, args...)
+        ValueList with_self;
+        with_self.push_back(fn);
+        for (int i = 0; i < args.size(); ++i) with_self.push_back(args[i]);
+        call_value(L, metamethod(fn, "__call"), with_self.data(), with_self.size(), out, &f, e->line);
+        return;
+    }
     if (!fn.is_function()) {
         std::string what;
         const Expr *c = e->l;
@@ -1449,6 +1502,7 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
                 Value keep = Value::object(Type::Table, t);  // the key expression may drop the last reference
                 eval(L, f, e->r, key);
                 out = t->get(key);
+                if (out.is_nil() && t->meta.is_table()) index_value(L, f, e, keep, key, out);   // __index
                 return;
             }
             Value obj = *po;
@@ -1527,6 +1581,12 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             }
             Value a = a_num ? Value(x0) : ta, b = *pb;
             double x, y;
+            if (a.is_table() || b.is_table()) {
+                static const char *const kEvent[] = {"__add", "__sub", "__mul", "__div", "__mod", "__pow"};
+                const char *ev = e->k == EK::Add ? kEvent[0] : e->k == EK::Sub ? kEvent[1] : e->k == EK::Mul ? kEvent[2]
+                                 : e->k == EK::Div ? kEvent[3] : e->k == EK::Mod ? kEvent[4] : kEvent[5];
+                if (call_binary(L, f, e->line, binary_handler(a, b, ev), a, b, out)) return;
+            }
             if (!coerce_num(a, &x)) {
                 std::string what = describe(e->l, f);
                 rt_error(f, e->line, std::string("attempt to ") + arith_name(e->k) + " a " + State::type_name(a) + " value" +
@@ -1544,6 +1604,7 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             Value a, b;
             eval(L, f, e->l, a);
             eval(L, f, e->r, b);
+            if ((a.is_table() || b.is_table()) && call_binary(L, f, e->line, binary_handler(a, b, "__concat"), a, b, out)) return;
             if (!(a.is_string() || a.is_number()))
                 rt_error(f, e->line, std::string("attempt to concatenate a ") + State::type_name(a) + " value");
             if (!(b.is_string() || b.is_number()))
@@ -1558,6 +1619,10 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             eval(L, f, e->l, a);
             eval(L, f, e->r, b);
             bool eq = a.raw_equals(b);
+            if (!eq && a.is_table() && b.is_table()) {   // __eq: only for two tables (5.2: handlers of either)
+                Value r;
+                if (call_binary(L, f, e->line, binary_handler(a, b, "__eq"), a, b, r)) eq = r.truthy();
+            }
             out = Value::boolean(e->k == EK::Eq ? eq : !eq);
             return;
         }
@@ -1590,10 +1655,10 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             }
             bool r;
             switch (e->k) {
-                case EK::Lt: r = less_than(f, e->line, a, b); break;
-                case EK::Le: r = less_equal(f, e->line, a, b); break;
-                case EK::Gt: r = less_than(f, e->line, b, a); break;
-                default: r = less_equal(f, e->line, b, a); break;
+                case EK::Lt: r = less_than(L, f, e->line, a, b); break;
+                case EK::Le: r = less_equal(L, f, e->line, a, b); break;
+                case EK::Gt: r = less_than(L, f, e->line, b, a); break;
+                default: r = less_equal(L, f, e->line, b, a); break;
             }
             out = Value::boolean(r);
             return;
@@ -1618,6 +1683,7 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             Value a;
             eval(L, f, e->l, a);
             double x;
+            if (a.is_table() && call_binary(L, f, e->line, metamethod(a, "__unm"), a, a, out)) return;
             if (!coerce_num(a, &x))
                 rt_error(f, e->line, std::string("attempt to perform arithmetic on a ") + State::type_name(a) + " value");
             out = Value(-x);
@@ -1627,6 +1693,7 @@ void eval(State &L, Frame &f, const Expr *e, Value &out) {
             Value a;
             eval(L, f, e->l, a);
             if (a.is_string()) out = Value(static_cast<double>(a.str().size()));
+            else if (a.is_table() && call_binary(L, f, e->line, metamethod(a, "__len"), a, a, out)) return;
             else if (a.is_table()) out = Value(static_cast<double>(static_cast<Table *>(a.obj())->length()));
             else rt_error(f, e->line, std::string("attempt to get length of a ") + State::type_name(a) + " value");
             return;
@@ -1681,6 +1748,21 @@ void assign_to(State &L, Frame &f, const Expr *target, const Value &v) {
                 rt_error(f, target->line, "attempt to index " + (what.empty() ? std::string("a ") : what + " (a ") +
                                               State::type_name(obj) + " value" + (what.empty() ? "" : ")"));
             }
+            // __newindex: consulted only when the key is absent from the table itself
+            for (int hops = 0; hops < 100 && obj.is_table(); ++hops) {
+                Table *t = static_cast<Table *>(obj.obj());
+                if (!t->meta.is_table() || !t->get(key).is_nil()) break;
+                Value h = metamethod(obj, "__newindex");
+                if (h.is_nil()) break;
+                if (h.is_function()) {
+                    const Value args[3] = {obj, key, v};
+                    ValueList rets;
+                    call_value(L, h, args, 3, rets, &f, target->line);
+                    return;
+                }
+                obj = h;   // a table: the assignment goes there (and may meet its metatable)
+            }
+            if (!obj.is_table()) rt_error(f, target->line, std::string("attempt to index a ") + State::type_name(obj) + " value");
             try {
                 static_cast<Table *>(obj.obj())->set(key, v);
             } catch (LuaError &err) {
@@ -2046,11 +2128,18 @@ void m_randomseed(State &, const Value *a, int n, ValueList &, void *ud) {
     rng->s = b ? b : 0x9E3779B97F4A7C15ull;
 }
 
+void b_tostring(State &L, const Value *a, int n, ValueList &out, void *);
 void b_print(State &L, const Value *a, int n, ValueList &, void *) {
     std::string line;
     for (int i = 0; i < n; ++i) {
         if (i) line += "\t";
-        line += State::tostring(a[i]);
+        if (a[i].is_table()) {   // may carry __tostring
+            ValueList s;
+            b_tostring(L, a + i, 1, s, nullptr);
+            line += s[0].str();
+        } else {
+            line += State::tostring(a[i]);
+        }
     }
     line += "\n";
     L.emit_print(line);
@@ -2061,7 +2150,34 @@ void b_type(State &L, const Value *a, int n, ValueList &out, void *) {
 }
 void b_tostring(State &L, const Value *a, int n, ValueList &out, void *) {
     if (n < 1) arg_error(1, "tostring", "value expected");
+    Value h = metamethod(a[0], "__tostring");
+    if (!h.is_nil()) {
+        ValueList rets;
+        L.call(h, a, 1, rets);
+        if (rets.size() < 1 || !(rets[0].is_string() || rets[0].is_number())) throw LuaError("'__tostring' must return a string");
+        out.push_back(rets[0].is_string() ? rets[0] : L.new_string(number_to_string(rets[0].num())));
+        return;
+    }
     out.push_back(L.new_string(State::tostring(a[0])));
+}
+void b_setmetatable(State &, const Value *a, int n, ValueList &out, void *) {
+    Table *t = check_table(a, n, 1, "setmetatable");
+    if (n < 2 || !(a[1].is_nil() || a[1].is_table())) arg_error(2, "setmetatable", "nil or table expected");
+    if (!metamethod(a[0], "__metatable").is_nil()) throw LuaError("cannot change a protected metatable");
+    t->meta = a[1];
+    out.push_back(a[0]);
+}
+void b_getmetatable(State &L, const Value *a, int n, ValueList &out, void *) {
+    if (n < 1) arg_error(1, "getmetatable", "value expected");
+    if (a[0].is_string()) {   // strings share one metatable whose __index is the string library
+        Value mt = L.new_table();
+        static_cast<Table *>(mt.obj())->set(L.new_string("__index"), L.get_global("string"));
+        out.push_back(mt);
+        return;
+    }
+    if (!a[0].is_table()) { out.push_back(Value()); return; }
+    Value prot = metamethod(a[0], "__metatable");
+    out.push_back(prot.is_nil() ? static_cast<Table *>(a[0].obj())->meta : prot);
 }
 void b_tonumber(State &, const Value *a, int n, ValueList &out, void *) {
     if (n < 1) arg_error(1, "tonumber", "value expected");
@@ -2866,6 +2982,7 @@ void for_each_child(Object *o, F &&fn) {
         }
         for (const Value &v : t->hash_order)
             if (v.type() >= Type::String) fn(v.obj());
+        if (t->meta.type() >= Type::String) fn(t->meta.obj());
     } else if (Function *f = dynamic_cast<Function *>(o)) {
         for (Box *b : f->upvals)
             if (b) fn(b);
@@ -2912,6 +3029,7 @@ void State::collect_cycles() {
             t->arr.clear();
             t->hash.clear();
             t->hash_order.clear();
+            t->meta = Value();
         } else if (Function *f = dynamic_cast<Function *>(o)) {
             std::vector<Box *> ups;
             ups.swap(f->upvals);
@@ -3063,6 +3181,8 @@ void State::open_libs() {
     register_function("collectgarbage", b_collectgarbage);
     register_function("load", b_load);
     register_function("loadstring", b_load);  // 5.1 name
+    register_function("setmetatable", b_setmetatable);
+    register_function("getmetatable", b_getmetatable);
     register_function("rawequal", b_rawequal);
     register_function("rawlen", b_rawlen);
     register_function("rawget", b_rawget);
@@ -3182,6 +3302,7 @@ struct Cloner {
                     t->hash.emplace(nk, clone(src->hash.find(k)->second));
                     t->hash_order.push_back(nk);
                 }
+                t->meta = clone(src->meta);
                 return tv;
             }
             case Type::Function: {

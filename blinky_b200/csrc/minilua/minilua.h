@@ -216,6 +216,7 @@ struct Table : Object {
     std::unordered_map<Value, Value, ValueHash, ValueEq> hash;
     // insertion-ordered key list of the hash part so iteration is deterministic
     std::vector<Value> hash_order;
+    Value meta;  // metatable (nil or a table): setmetatable / getmetatable
 
     Value get(const Value &k) const;
     Value get_int(int64_t i) const;

@@ -262,6 +262,60 @@ assert(not pcall(string.gsub, "a", "a", "%2"))
 """)
 
 
+def test_metatables(lua):
+    """setmetatable / getmetatable and the events a math-heavy script would use: __index (table chain and function),
+    __newindex, arithmetic, __unm, __eq, __lt, __le, __len, __concat, __call, __tostring, protected metatables"""
+    out = ok(lua, """
+local V = {}
+V.__index = V
+local function vec(x, y, z) return setmetatable({x = x, y = y, z = z}, V) end
+V.__add = function(a, b) return vec(a.x + b.x, a.y + b.y, a.z + b.z) end
+V.__sub = function(a, b) return vec(a.x - b.x, a.y - b.y, a.z - b.z) end
+V.__mul = function(a, b)
+  if type(a) == "number" then return vec(a * b.x, a * b.y, a * b.z) end
+  if type(b) == "number" then return vec(a.x * b, a.y * b, a.z * b) end
+  return a.x * b.x + a.y * b.y + a.z * b.z
+end
+V.__div = function(a, b) return vec(a.x / b, a.y / b, a.z / b) end
+V.__unm = function(a) return vec(-a.x, -a.y, -a.z) end
+V.__eq = function(a, b) return a.x == b.x and a.y == b.y and a.z == b.z end
+V.__lt = function(a, b) return a:len() < b:len() end
+V.__le = function(a, b) return a:len() <= b:len() end
+V.__len = function(a) return 3 end
+V.__tostring = function(a) return "(" .. a.x .. "," .. a.y .. "," .. a.z .. ")" end
+V.__concat = function(a, b) return tostring(a) .. tostring(b) end
+V.__call = function(a, k) return a[k] end
+function V.len(a) return math.sqrt(a * a) end
+local a, b = vec(1, 2, 3), vec(4, 5, 6)
+assert(tostring(a + b) == "(5,7,9)" and tostring(b - a) == "(3,3,3)" and a * b == 32)
+assert(tostring(2 * a) == "(2,4,6)" and tostring(a * 2) == "(2,4,6)" and tostring(-a) == "(-1,-2,-3)" and tostring(b / 2) == "(2,2.5,3)")
+assert(a == vec(1, 2, 3) and a ~= b and a < b and a <= b and not (a > b) and b >= a)
+assert(#a == 3 and a .. b == "(1,2,3)(4,5,6)" and a("y") == 2 and math.abs(a:len() - 3.7416573867739) < 1e-12)
+local log = {}
+local t = setmetatable({}, {__index = function(t, k) return k .. "!" end,
+                            __newindex = function(t, k, v) rawset(t, k, v * 2) log[#log + 1] = k end})
+t.a = 5
+t.a = 7   -- present now: plain assignment
+assert(t.a == 7 and t.zzz == "zzz!" and rawget(t, "zzz") == nil and #log == 1)
+local store = {}
+local proxy = setmetatable({}, {__newindex = store, __index = store})
+proxy.k = 1
+assert(rawget(proxy, "k") == nil and store.k == 1 and proxy.k == 1)
+local Base = {hello = function() return "base" end}
+Base.__index = Base
+local Derived = setmetatable({}, Base)
+Derived.__index = Derived
+local obj = setmetatable({}, Derived)
+assert(obj.hello() == "base" and getmetatable(obj) == Derived and getmetatable("x").__index == string)
+local p = setmetatable({}, {__metatable = "locked"})
+assert(getmetatable(p) == "locked" and not pcall(setmetatable, p, {}))
+assert(not pcall(function() return {} + 1 end))
+assert(setmetatable(obj, nil) == obj and getmetatable(obj) == nil and obj.hello == nil)
+print(a, 1)
+""")
+    assert out == "(1,2,3)\t1\n"
+
+
 def test_base_library_corners(lua):
     """xpcall, load, collectgarbage and the harmless corners of os / io (the reference opens all libraries,
     fisheye.c:1228; file access stays out)"""
